@@ -1,0 +1,348 @@
+"""CPU restatement of the WALNUTSpy transition kernel.  TEST INFRASTRUCTURE ONLY.
+
+Restates reference WALNUTSpy/WALNUTS.py:111-727 (driver) and
+WALNUTSpy/adaptiveIntegrators.py:49-137,361-475 (fixedLeapFrog, adaptLeapFrogD,
+adaptLeapFrogR2P) in the streaming form the CUDA kernels use:
+
+  * the post-order sub-U-turn plan (WALNUTS.py:22-41) is derived from the leaf counter
+    (after even leaf n: one check per s>=1 with n % 2**s == 0, span [n-2**s+1, n]);
+  * only the left-end (q, v) of each pending dyadic level is kept (WALNUTS.py:48-88 keeps
+    both ends of every finished subtree; only the left ends are ever read, :575-587);
+  * running min/max replace the 2**M arrays Hs/Ifs/Ibs/cs/lwts (WALNUTS.py:170-174).
+
+Pinned against the reference itself: tests/test_oracle_vs_reference.py runs the real
+WALNUTS.py (when /root/reference is present) under the same RNG and requires bit-identical
+samples and diagnostics; tests/golden/*.npz hold reference outputs for boxes without it.
+
+All reference quirks of SURVEY.md row A14 are reproduced (cited inline).
+"""
+import math
+
+import numpy as np
+
+LOG_ZERO = -700.0                       # constants.py:13
+WT_SUM_THRESH = float(np.exp(LOG_ZERO + 1.0))   # constants.py:14
+
+FIXED, ADAPT_D, ADAPT_R2P = 0, 1, 2
+
+
+class AuxPar:
+    """adaptiveIntegrators.integratorAuxPar (adaptiveIntegrators.py:36-44), hot-path fields."""
+
+    def __init__(self, minC=0, maxC=10, R2Pprob0=2.0 / 3.0):
+        self.minC, self.maxC, self.R2Pprob0 = minC, maxC, R2Pprob0
+
+
+def _pysum(x):
+    # the reference uses the Python builtin sum() (strict left-to-right) for sum(v*v) and the
+    # U-turn dots (WALNUTS.py:97,256; adaptiveIntegrators.py:55,84)
+    return sum(x)
+
+
+def stop_condition(qm, vm, qp, vp):
+    """WALNUTS.py:95-97."""
+    tmp = qp - qm
+    return bool(_pysum(vp * tmp) < 0.0 or _pysum(vm * tmp) < 0.0)
+
+
+def _pass(q, vv, g, h, c, lpFun, track):
+    """2**c leapfrog micro-steps of total length h (adaptiveIntegrators.py:70-84).
+    Returns (q, vv, g, f, H_last, all_finite, max|diff H|)."""
+    nstep = 2 ** c
+    hh = h / nstep
+    Hprev = track
+    ok = True
+    maxd = 0.0
+    f = None
+    for _ in range(nstep):
+        vh = vv + 0.5 * hh * g
+        q = q + hh * vh
+        f, g = lpFun(q)
+        vv = vh + 0.5 * hh * g
+        Hk = -f + 0.5 * _pysum(vv * vv)
+        ok = ok and bool(np.isfinite(Hk))
+        dd = abs(Hk - Hprev)
+        maxd = dd if (dd > maxd or dd != dd) else maxd
+        Hprev = Hk
+    return q, vv, g, f, Hprev, ok, maxd, hh
+
+
+def macro_step(kind, q, v, g, Ham0, h, xi, lpFun, delta, aux, rng):
+    """One macro step.  Returns dict(q, v, grad, H, nF, nB, If, Ib, c, lwt, igrConst).
+    `v` is in forward-time convention in and out (adaptiveIntegrators.py:73,135)."""
+    vv0 = xi * v
+    if kind == FIXED:                               # adaptiveIntegrators.py:49-59
+        vh = vv0 + 0.5 * h * g
+        qq = q + h * vh
+        f, gn = lpFun(qq)
+        vv = vh + 0.5 * h * gn
+        H1 = -f + 0.5 * _pysum(vv * vv)
+        with np.errstate(all="ignore"):
+            igr = h * (max(1.0e-10, abs(Ham0 - H1)) ** (-1.0 / 3.0))
+        return dict(q=qq, v=xi * vv, grad=gn, H=H1, nF=1, nB=0, If=0, Ib=0, c=0, lwt=0.0, igrConst=igr)
+
+    minC, maxC = aux.minC, aux.maxC
+    nF = 0
+    If = maxC
+    for c in range(minC, maxC + 1):                 # :69-94 / :365-389
+        qq, vv, gg, f, Hl, ok, maxd, hh = _pass(q, vv0, g, h, c, lpFun, Ham0)
+        nF += 2 ** c
+        if ok and abs(Ham0 - Hl) < delta:
+            If = c
+            break
+    cSim = If
+    lwtf = 0.0
+    if kind == ADAPT_R2P:
+        if rng.uniform() < aux.R2Pprob0:            # :392
+            lwtf = math.log(aux.R2Pprob0)
+        else:                                       # :400-424 redo at If+1
+            cSim = If + 1
+            qq, vv, gg, f, Hl, ok, maxd, hh = _pass(q, vv0, g, h, cSim, lpFun, Ham0)
+            nF += 2 ** cSim
+            lwtf = math.log(1.0 - aux.R2Pprob0)
+    qO, vO, gO, HO = qq, vv, gg, Hl
+    with np.errstate(all="ignore"):
+        igr = hh * (maxd ** (-1.0 / 3.0)) if maxd > 0 else np.inf   # :101,399,424
+
+    if kind == ADAPT_D or cSim == If:               # :104-132 / :430-433
+        maxTry, Ib = If - 1, If
+    else:                                           # :434-437
+        maxTry, Ib = maxC, maxC
+    nB = 0
+    for c in range(minC, maxTry + 1):               # :111-132 / :444-464
+        _, _, _, _, Hb, okb, _, _ = _pass(qO, -vO, gO, h, c, lpFun, HO)
+        nB += 2 ** c
+        if okb and abs(HO - Hb) < delta:
+            Ib = c
+            break
+    if kind == ADAPT_D:
+        lwt = (If != Ib) * LOG_ZERO                 # :136
+    else:                                           # :467-475
+        lwtb = LOG_ZERO
+        if cSim == Ib:
+            lwtb = math.log(aux.R2Pprob0)
+        elif cSim == Ib + 1:
+            lwtb = math.log(1.0 - aux.R2Pprob0)
+        lwt = lwtb - lwtf
+    return dict(q=qO, v=xi * vO, grad=gO, H=HO, nF=nF, nB=nB, If=If, Ib=Ib, c=cSim, lwt=lwt, igrConst=igr)
+
+
+def transition(lpFun, qc, rng, kind, H, delta, M, aux, jitter=0.2, igr_sink=None):
+    """One WALNUTSpy iteration (WALNUTS.py:196-693).  Returns (q_next, diag[24])."""
+    d = qc.size
+    B = np.floor(rng.dir_uniform02(M)).astype(int)                      # :216
+    v = rng.normal(d)                                                   # :236
+    f0, g0 = lpFun(qc)                                                  # :249
+    H0 = -f0 + 0.5 * _pysum(v ** 2)                                     # :256
+    # ends: index 0 = plus (forward) end, 1 = minus (backward) end
+    end_q = [qc, qc]
+    end_v = [v, v]
+    end_g = [g0, g0]
+    end_H = [H0, H0]
+    lwtSum = [0.0, 0.0]                 # [f, b]
+    timeLen = [0.0, 0.0]                # [F, B]
+    maxInt = [0, 0]                     # maxFint, maxBint
+    WoldSum = 1.0
+    qProp = qc
+    L_ = 0
+    indexStat = 0.0
+    orbitLen = orbitLenSam = 0.0
+    nF = nB = 0
+    NdS = NdC = 0
+    stopCode = 0
+    bothEndsPassive = False
+    # running statistics over used steps (WALNUTS.py:660-692)
+    st = dict(n=0, minIf=None, maxIf=None, minl=None, maxl=None, minc=None, maxc=None,
+              nne=0, nz=0, Hmax=H0, Hmin=H0, Hnan=False)
+    lo = H * (1 - jitter)
+    hi = H * (1 + jitter)
+
+    def record(o):
+        st["n"] += 1
+        for k, val in (("If", o["If"]), ("l", o["lwt"]), ("c", o["c"])):
+            st["min" + k] = val if st["min" + k] is None else min(st["min" + k], val)
+            st["max" + k] = val if st["max" + k] is None else max(st["max" + k], val)
+        st["nne"] += int(o["If"] != o["Ib"])
+        st["nz"] += int(o["If"] == 0)
+        if o["H"] != o["H"]:
+            st["Hnan"] = True
+        else:
+            st["Hmax"] = max(st["Hmax"], o["H"])
+            st["Hmin"] = min(st["Hmin"], o["H"])
+
+    forced = False
+    for i in range(M):                                                  # :281
+        side = int(B[i])                # 0 forward, 1 backward
+        xi = 1 - 2 * side
+        n_new = 2 ** i
+        qPropLast, Lold, indexStatOld = qProp, L_, indexStat
+        WnewSum = 0.0
+        expand = True
+        left = {}                       # level -> (q, v) left ends of pending dyadic spans
+        hpair = None
+        for n in range(1, n_new + 1):
+            if i == 0:
+                h = float(rng.uniform_range(lo, hi, 1)[0])              # :298
+                orbitLen += h                                           # :300
+            elif n % 2 == 1:
+                hpair = rng.uniform_range(lo, hi, 2)                    # :395
+                h = float(hpair[0])
+            else:
+                h = float(hpair[1])
+            o = macro_step(kind, end_q[side], end_v[side], end_g[side], end_H[side], h, xi,
+                           lpFun, delta, aux, rng)
+            end_q[side], end_v[side], end_g[side], end_H[side] = o["q"], o["v"], o["grad"], o["H"]
+            nF += o["nF"]
+            nB += o["nB"]
+            if igr_sink is not None:
+                igr_sink(o["igrConst"])                                 # :313 (warm-up only)
+            idx = maxInt[side] + xi if i > 0 else xi
+            maxInt[side] = idx
+            if i == 0:
+                timeLen[side] = h                                       # :315,349
+            else:
+                timeLen[side] += h                                      # :413,456,500,543
+            record(o)
+            if not np.isfinite(o["H"]):                                 # :316,350,414,457,501,544
+                forced = True
+                if i == 0 or n % 2 == 1:
+                    stopCode = 999      # quirk A14(ii): second leaf of a pair leaves stopCode as is
+                break
+            if i == 0:
+                lwtSum[side] = o["lwt"]                                 # :321,354
+            elif not (side == 1 and n % 2 == 0):
+                lwtSum[side] += o["lwt"]    # quirk A14(i): :420 has no counterpart after :443-459
+            Wnew = float(np.exp(-o["H"] + H0 + lwtSum[side]))           # :322,355,422,462,510,552
+            if i == 0:
+                WnewSum = Wnew
+                qProp, L_, indexStat = o["q"], xi, xi * timeLen[side]   # :326-328,359-361
+            else:
+                WnewSum += Wnew
+                if WnewSum > WT_SUM_THRESH and rng.uniform() < Wnew / WnewSum:   # :426,464,512,554
+                    qProp, L_, indexStat = o["q"], idx, xi * timeLen[side]
+                orbitLen += h                                           # :432,471,519,561
+                if n % 2 == 1:
+                    # left end of levels 1..tz(n-1) (all levels when n == 1): one slot suffices
+                    lvl = i if n == 1 else ((n - 1) & -(n - 1)).bit_length() - 1
+                    left[lvl] = (o["q"], o["v"])
+                else:
+                    s = 1
+                    while s <= i and n % (2 ** s) == 0:
+                        m = n - 2 ** s + 1
+                        lvl = i if m == 1 else ((m - 1) & -(m - 1)).bit_length() - 1
+                        ql, vl = left[lvl]
+                        if xi == 1:
+                            ut = stop_condition(ql, vl, o["q"], o["v"])          # :568,582
+                        else:
+                            ut = stop_condition(o["q"], o["v"], ql, vl)          # :479,582
+                        if ut:
+                            expand = False
+                            break
+                        s += 1
+                    if not expand:
+                        break
+        if forced:                                                      # :590-592 (quirk A14(iii))
+            break
+        with np.errstate(all="ignore"):
+            indexStat = indexStat / (timeLen[0] + timeLen[1])           # :595
+        if not expand:                                                  # :597-605
+            qProp, L_, indexStat = qPropLast, Lold, indexStatOld
+            NdS, NdC, stopCode = i, i + 1, 5
+            break
+        if not (rng.uniform() < WnewSum / WoldSum):                     # :613
+            qProp, L_, indexStat = qPropLast, Lold, indexStatOld
+        joined = stop_condition(end_q[1], end_v[1], end_q[0], end_v[0])  # :622
+        bothEndsPassive = lwtSum[1] < LOG_ZERO + 1.0 and lwtSum[0] < LOG_ZERO + 1.0   # :624
+        if joined or bothEndsPassive:
+            stopCode = 4 if joined else -4
+            NdS = NdC = i + 1
+            orbitLenSam = orbitLen
+            break
+        WoldSum += WnewSum                                              # :641
+        orbitLenSam = orbitLen
+        NdS = NdC = i + 1
+
+    diag = np.zeros(24)
+    n = st["n"]
+    diag[0] = L_
+    diag[1] = NdS
+    diag[2] = orbitLen
+    diag[3] = orbitLenSam
+    diag[4] = maxInt[0]
+    diag[5] = maxInt[1]
+    diag[6] = nF
+    diag[7] = nB
+    diag[8], diag[9] = st["minIf"], st["maxIf"]
+    diag[10], diag[11] = st["minl"], st["maxl"]
+    diag[12] = 1.0 * bothEndsPassive
+    diag[13] = 1.0 * (lwtSum[1] < LOG_ZERO + 1.0 or lwtSum[0] < LOG_ZERO + 1.0)
+    diag[14] = st["nne"] / n
+    diag[15] = H
+    diag[16] = st["nz"] / n
+    diag[17] = np.nan if st["Hnan"] else st["Hmax"] - st["Hmin"]
+    diag[18] = delta
+    diag[19] = 1.0 * stopCode
+    diag[20] = NdC
+    diag[21], diag[22] = st["minc"], st["maxc"]
+    diag[23] = indexStat
+    return qProp, diag
+
+
+class PhiloxRNG:
+    """Adapter: oracle.philox.ChainStreams -> the rng protocol used by transition()."""
+
+    def __init__(self, streams):
+        self.s = streams
+
+    def dir_uniform02(self, M):
+        return 2.0 * self.s.directions(M)
+
+    def normal(self, d):
+        return self.s.momentum(d)
+
+    def uniform_range(self, lo, hi, size):
+        return np.array([lo + (hi - lo) * self.s.uniform() for _ in range(size)])
+
+    def uniform(self):
+        return self.s.uniform()
+
+
+class NumpyGlobalRNG:
+    """Adapter over numpy's legacy global RNG, call-for-call as the reference uses it."""
+
+    def dir_uniform02(self, M):
+        return np.random.uniform(low=0.0, high=2.0, size=M)
+
+    def normal(self, d):
+        return np.random.normal(size=d)
+
+    def uniform_range(self, lo, hi, size):
+        return np.random.uniform(low=lo, high=hi, size=size)
+
+    def uniform(self):
+        return np.random.uniform()
+
+
+def WALNUTS(lpFun, q0, generated=lambda q: q, integrator=FIXED, H0=0.2, stepSizeRandScale=0.2,
+            delta0=0.05, numIter=2000, M=10, igrAux=None, rng=None, seed=0, chain=0,
+            first_iteration=1):
+    """Fixed-(H, delta) WALNUTSpy chain (warmupIter=0, adaptH=adaptDelta=False).
+    Returns (samples (dg, numIter+1), diagnostics (numIter, 24)) like WALNUTS.py:724-727."""
+    from . import philox
+    aux = igrAux or AuxPar()
+    streams = None
+    if rng is None:
+        streams = philox.ChainStreams(seed, chain)
+        rng = PhiloxRNG(streams)
+    qc = np.asarray(q0, dtype=np.float64)
+    g0 = generated(qc)
+    samples = np.zeros((g0.size, numIter + 1))
+    samples[:, 0] = g0
+    diagnostics = np.zeros((numIter, 24))
+    for it in range(1, numIter + 1):
+        if streams is not None:
+            streams.begin_iteration(first_iteration + it - 1)
+        qc, diagnostics[it - 1] = transition(lpFun, qc, rng, integrator, H0, delta0, M, aux,
+                                             jitter=stepSizeRandScale)
+        samples[:, it] = generated(qc)
+    return samples, diagnostics
