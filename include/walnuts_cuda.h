@@ -1,0 +1,142 @@
+/*
+ * walnuts_cuda.h -- C-ABI of the B200-native many-chain WALNUTS/NUTS sampler.
+ *
+ * The reference (bob-carpenter/walnuts) is pure Python and has no FFI layer for this path, so
+ * the boundary below is what its two Python call surfaces bind through ctypes
+ * (see INTEGRATION.md for the stub a reference maintainer would add):
+ *
+ *   walnuts(rng, theta_init, logp, grad, inv_mass, macro_step, max_nuts_depth, max_error,
+ *           iter_warmup, iter_sample)                     reference walnuts/walnuts.py:362-408
+ *   walnuts_step(...)                                     reference walnuts/walnuts.py:279-359
+ *   WALNUTS(lpFun, q0, generated, integrator, H0, stepSizeRandScale, delta0, numIter,
+ *           warmupIter, M, igrAux, ...)                   reference WALNUTSpy/WALNUTS.py:111-727
+ *   integrator protocol fixedLeapFrog / adaptLeapFrogD / adaptLeapFrogR2P
+ *                                                         reference WALNUTSpy/adaptiveIntegrators.py:49-137,361-475
+ *   lpFun(q) -> [lp, grad] / logp(theta), grad(theta)     reference WALNUTSpy/targetDistr.py:18-92, test/targets.py:4-29
+ *
+ * Conventions: every entry point returns 0 on success and a negative WN_E* code on failure
+ * (no exceptions / exit() across the ABI; the reference's sys.exit("stack full"),
+ * WALNUTS.py:65, and ValueError, walnuts.py:309-320, become error codes + wn_last_error()).
+ * The caller owns every buffer.  One handle per (device, host thread); each handle owns one
+ * CUDA stream.  Per-chain numerical failures are reported in the diagnostics stop-code column
+ * (999, WALNUTS.py:318), never as a call failure.  All floating-point data is IEEE fp64.
+ */
+#ifndef WALNUTS_CUDA_H
+#define WALNUTS_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WN_ABI_VERSION 1
+
+/* error codes */
+#define WN_OK 0
+#define WN_EINVAL (-1)   /* bad argument (the reference raises ValueError, walnuts.py:309-320) */
+#define WN_ECUDA (-2)    /* CUDA runtime error; text in wn_last_error() */
+#define WN_ENOMEM (-3)
+#define WN_EUNSUPPORTED (-4) /* target/dimension/mode combination has no kernel */
+#define WN_ESTATE (-5)   /* call order violation (e.g. wn_run before wn_set_state) */
+
+/* targets: the registry that replaces WALNUTSpy/targetDistr.py and test/targets.py */
+#define WN_TARGET_STD_NORMAL 0   /* targetDistr.stdGauss :18-21, test/targets.py:4-7          */
+#define WN_TARGET_DIAG_GAUSS 1   /* lp = -1/2 sum q_i^2 inv_var_i; data key "inv_var" [d]     */
+#define WN_TARGET_FUNNEL 2       /* targetDistr.funnel10 :74-78 generalised to d = 1 + n      */
+#define WN_TARGET_LOGREG 3       /* Bernoulli-logit + N(0,tau^2) prior; keys "X" [N,P], "y" [N] */
+#define WN_TARGET_STOCK_WATSON 4 /* WALNUTSpy_examples/StockWatson/sw_innov.stan; key "y" [T] */
+#define WN_TARGET_CORR_GAUSS 5   /* targetDistr.corrGauss :25-31 (2-d, rho = 0.5)             */
+#define WN_TARGET_FUNNEL_PKG 6   /* test/targets.py:23-29 (different density from funnel10)   */
+
+/* transition semantics */
+#define WN_MODE_WALNUTSPY 0 /* WALNUTSpy/WALNUTS.py + adaptiveIntegrators.py */
+#define WN_MODE_PACKAGE 1   /* walnuts/walnuts.py */
+
+/* macro-step integrators (WALNUTSPY mode) */
+#define WN_INT_FIXED 0 /* adaptiveIntegrators.fixedLeapFrog     :49-59   (plain NUTS)        */
+#define WN_INT_D 1     /* adaptiveIntegrators.adaptLeapFrogD    :65-137                      */
+#define WN_INT_R2P 2   /* adaptiveIntegrators.adaptLeapFrogR2P  :361-475                     */
+
+#define WN_DIAG_COLS 24 /* WALNUTS.py:180,670-693 */
+
+typedef struct wn_handle wn_handle;
+
+typedef struct wn_config {
+  int32_t target;      /* WN_TARGET_*                                                    */
+  int32_t mode;        /* WN_MODE_*                                                      */
+  int32_t integrator;  /* WN_INT_* (WALNUTSPY mode)                                      */
+  int32_t d;           /* dimension of q / theta                                         */
+  int32_t n_chains;    /* chains held by this handle (this GPU's shard)                  */
+  int32_t device;      /* CUDA device ordinal                                            */
+  int32_t dg;          /* leading coordinates stored per draw (generated = q[0:dg])      */
+  int32_t M;           /* max doublings: WALNUTS(M=) / walnuts(max_nuts_depth=)          */
+  int32_t minC, maxC;  /* integratorAuxPar.minC / maxC, adaptiveIntegrators.py:36-44     */
+  int32_t compat;      /* PACKAGE mode: 1 = reproduce reference defects B3/B5*/
+  int32_t reserved0;
+  double H0;           /* macro step: WALNUTS(H0=) / walnuts(macro_step=)                */
+  double jitter;       /* WALNUTS(stepSizeRandScale=), WALNUTS.py:298,395                */
+  double delta;        /* WALNUTS(delta0=) / walnuts(max_error=)                         */
+  double r2p_prob0;    /* integratorAuxPar.R2Pprob0                                      */
+  double log_p0;       /* log(r2p_prob0), computed by the caller's libm (bit parity)     */
+  double log_1mp0;     /* log(1 - r2p_prob0)                                             */
+  uint64_t seed;       /* Philox key                                                     */
+  uint64_t chain_offset; /* global id of this handle's chain 0 (multi-GPU sharding)      */
+} wn_config;
+
+int wn_abi_version(void);
+
+/* name -> WN_TARGET_* ("std_normal","diag_gauss","funnel","logreg","stock_watson",
+ * "corr_gauss","funnel_pkg"); <0 if unknown. */
+int wn_target_id(const char* name);
+
+int wn_create(const wn_config* cfg, wn_handle** out);
+void wn_destroy(wn_handle* h);
+
+/* Target data / per-chain tuning.  `key`: "inv_var" [d], "inv_mass" [d] (PACKAGE mode metric,
+ * walnuts.py:298), "X" [N*P row-major], "y" [N or T], "tau" [1], "H" [n_chains] and "delta"
+ * [n_chains] (per-chain macro step / tolerance, overriding cfg.H0 / cfg.delta).
+ * `on_device` != 0: `ptr` is a device pointer on cfg.device. */
+int wn_set_data(wn_handle* h, const char* key, const double* ptr, int64_t n, int on_device);
+
+/* Positions of all chains, row-major [n_chains, d]. */
+int wn_set_state(wn_handle* h, const double* q, int on_device);
+int wn_get_state(wn_handle* h, double* q, int on_device);
+
+/* Run n_iter transitions of every chain.
+ *   draws  [n_iter, n_chains, dg] or NULL
+ *   diag   [n_iter, n_chains, WN_DIAG_COLS] or NULL  (columns as WALNUTS.py:670-693)
+ *   nevalF, nevalB [n_chains] or NULL: gradient evaluations of this call (forward / reversibility
+ *   passes; the one evaluation at the start of each iteration, WALNUTS.py:249, is not counted,
+ *   like the reference).
+ * Iterations continue the Philox streams of earlier calls on the same handle. */
+int wn_run(wn_handle* h, int64_t n_iter, double* draws, double* diag, uint64_t* nevalF,
+           uint64_t* nevalB, int on_device);
+
+/* Same, asynchronous on the handle's stream with device buffers only; pair with wn_sync(). */
+int wn_run_async(wn_handle* h, int64_t n_iter, double* d_draws, double* d_diag,
+                 uint64_t* d_nevalF, uint64_t* d_nevalB);
+int wn_sync(wn_handle* h);
+
+/* Device time of the last wn_run / wn_run_async kernel in milliseconds (CUDA events on the
+ * handle's stream), its launch count, and the total gradient evaluations it performed. */
+int wn_last_kernel_ms(wn_handle* h, float* ms);
+int wn_last_launches(wn_handle* h, int64_t* n);
+int wn_last_grad_evals(wn_handle* h, uint64_t* forward, uint64_t* backward);
+
+/* Cross-chain moments of the current state over this handle's chains: mean[d], var[d]
+ * (unbiased).  Multi-GPU callers reduce (n, sum, sumsq) themselves. */
+int wn_moments(wn_handle* h, double* mean, double* var);
+
+/* the CUDA stream (cudaStream_t) owned by the handle, for event timing by the caller */
+void* wn_stream(wn_handle* h);
+
+const char* wn_last_error(const wn_handle* h);
+
+/* FP64 FMA throughput micro-benchmark (roofline denominator): returns achieved FLOP/s. */
+int wn_fp64_peak(int device, double* flops_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WALNUTS_CUDA_H */

@@ -1,0 +1,21 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "slow: long-running statistical test")
+
+
+@pytest.fixture(scope="session")
+def cuda_lib():
+    """Build (if stale) and load the CUDA library; GPU tests fail loudly without it."""
+    from walnuts_b200 import _ffi, build
+    build.build()
+    return _ffi.load()

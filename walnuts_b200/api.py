@@ -1,0 +1,132 @@
+"""Drop-in call surfaces of the reference, running on CUDA.
+
+WALNUTS(...)  : reference WALNUTSpy/WALNUTS.py:111-727
+walnuts(...)  : reference walnuts/walnuts.py:362-408;  walnuts_step(...) : walnuts.py:279-359
+
+Differences a caller sees: `lpFun` / `logp` / `integrator` are registry handles
+(walnuts_b200.targets / walnuts_b200.integrators) instead of Python callables; `q0` / `theta_init`
+may carry a leading chains axis (n_chains, d), in which case every output gains a leading chains
+axis; randomness comes from per-chain Philox streams keyed by `seed` (drawn from numpy's global RNG,
+respectively from `rng`, when not given -- so `np.random.seed(k)` still makes runs reproducible).
+"""
+import numpy as np
+
+from . import integrators as _ig
+from . import targets as _tg
+from .sampler import ChainBatch
+
+
+def _seed_from_global():
+    return int(np.random.randint(0, 2 ** 62))
+
+
+def WALNUTS(lpFun, q0, generated=None, integrator=_ig.fixedLeapFrog, H0=0.2, stepSizeRandScale=0.2,
+            delta0=0.05, numIter=2000, warmupIter=1000, M=10, igrAux=None, adaptH=True,
+            adaptHtarget=0.8, adaptDelta=True, adaptDeltaTarget=0.6, adaptDeltaQuantile=0.9,
+            recordOrbitStats=False, *, seed=None, device=0, chain_offset=0):
+    """Many-chain WALNUTS/NUTS with the WALNUTSpy driver semantics (WALNUTS.py:111-129 arguments).
+
+    Returns (samples, diagnostics): for a single chain (`q0.ndim == 1`) shapes are (dg, numIter+1) and
+    (numIter, 24) exactly as WALNUTS.py:163,180,724-727; with q0 of shape (n_chains, d) a leading
+    chains axis is added.
+    """
+    if adaptH and (adaptHtarget < 0.0 or adaptHtarget > 1.0):
+        raise ValueError("bad adaptHtarget")          # sys.exit in the reference, WALNUTS.py:140
+    if adaptDelta and adaptDeltaTarget < 0.0:
+        raise ValueError("bad adaptDeltaTarget")      # WALNUTS.py:146
+    if warmupIter > 0 and (adaptH or adaptDelta):
+        raise NotImplementedError(
+            "warm-up adaptation of H/delta (WALNUTS.py:701-712) is not on the GPU yet (SURVEY.md row N1): "
+            "call with warmupIter=0 or adaptH=False, adaptDelta=False and fixed H0/delta0")
+    if recordOrbitStats:
+        raise NotImplementedError("recordOrbitStats (WALNUTS.py:182-184) is not implemented (SURVEY.md row N2)")
+    if not isinstance(integrator, _ig._Integrator):
+        raise TypeError("integrator must be one of walnuts_b200.fixedLeapFrog / adaptLeapFrogD / adaptLeapFrogR2P")
+    aux = igrAux or _ig.integratorAuxPar()
+    q0 = np.asarray(q0, dtype=np.float64)
+    single = q0.ndim == 1
+    q = q0.reshape(1, -1) if single else q0
+    n_chains, d = q.shape
+    name, data = _tg.resolve(lpFun, d)
+    if seed is None:
+        seed = _seed_from_global()
+    with ChainBatch(name, d, n_chains, mode="walnutspy", integrator=integrator.kind, H0=H0,
+                    jitter=stepSizeRandScale, delta=delta0, M=M, minC=aux.minC, maxC=aux.maxC,
+                    r2p_prob0=aux.R2Pprob0, seed=seed, chain_offset=chain_offset, device=device,
+                    data=data) as cb:
+        cb.set_state(q)
+        out = cb.run(numIter, draws=True, diag=True)
+    draws = out["draws"]                                    # (numIter, n_chains, d)
+    gen = generated if generated is not None else (lambda x: x)
+    g0 = np.asarray(gen(q[0]))
+    samples = np.empty((n_chains, g0.size, numIter + 1))
+    if generated is None:
+        samples[:, :, 0] = q
+        samples[:, :, 1:] = np.transpose(draws, (1, 2, 0))
+    else:
+        for c in range(n_chains):
+            samples[c, :, 0] = gen(q[c])
+            for i in range(numIter):
+                samples[c, :, i + 1] = gen(draws[i, c])
+    diagnostics = np.ascontiguousarray(np.transpose(out["diag"], (1, 0, 2)))   # (n_chains, numIter, 24)
+    if single:
+        return samples[0], diagnostics[0]
+    return samples, diagnostics
+
+
+def _pkg_batch(rng, theta, logp, grad, inv_mass, macro_step, max_nuts_depth, max_error, seed, device,
+               compat, chain_offset):
+    theta = np.array(theta, dtype=np.float64)
+    inv_mass = np.array(inv_mass, dtype=np.float64)
+    single = theta.ndim == 1
+    if theta.ndim not in (1, 2):
+        raise ValueError("theta not a vector")                      # walnuts.py:309-310
+    if inv_mass.ndim != 1:
+        raise ValueError("inv_mass not a vector")                   # :311-312
+    th = theta.reshape(1, -1) if single else theta
+    if th.shape[1] != inv_mass.size:
+        raise ValueError("size mismatch between theta and inv_mass")  # :313-314
+    if not macro_step > 0:
+        raise ValueError("non-positive macro_step")                 # :315-316
+    if not max_nuts_depth > 0:
+        raise ValueError("non-positive max_nuts_depth")             # :317-318
+    if not max_error > 0:
+        raise ValueError("non-positive max_error")                  # :319-320
+    if logp is not grad and not (isinstance(logp, _tg.Target) and isinstance(grad, _tg.Target)
+                                 and logp.name == grad.name):
+        raise TypeError("logp and grad must be the same walnuts_b200.targets handle")
+    name, data = _tg.resolve(logp, th.shape[1])
+    if seed is None:
+        seed = int(rng.integers(0, 2 ** 62)) if hasattr(rng, "integers") else int(rng)
+    data = dict(data)
+    data["inv_mass"] = inv_mass
+    cb = ChainBatch(name, th.shape[1], th.shape[0], mode="package", H0=macro_step, delta=max_error,
+                    M=max_nuts_depth, seed=seed, chain_offset=chain_offset, device=device, compat=compat,
+                    data=data)
+    cb.set_state(th)
+    return cb, single
+
+
+def walnuts(rng, theta_init, logp, grad, inv_mass, macro_step, max_nuts_depth, max_error, iter_warmup,
+            iter_sample, *, seed=None, device=0, compat=True, chain_offset=0):
+    """walnuts.py:362-408.  Returns draws (iter_sample, D), or (n_chains, iter_sample, D) when
+    `theta_init` has a leading chains axis."""
+    cb, single = _pkg_batch(rng, theta_init, logp, grad, inv_mass, macro_step, max_nuts_depth, max_error,
+                            seed, device, compat, chain_offset)
+    with cb:
+        if iter_warmup > 0:
+            cb.run(iter_warmup, draws=False, nevals=False)
+        draws = cb.run(iter_sample, draws=True, nevals=False)["draws"]   # (iter, chains, D)
+    draws = np.ascontiguousarray(np.transpose(draws, (1, 0, 2)))
+    return draws[0] if single else draws
+
+
+def walnuts_step(rng, theta, logp, grad, inv_mass, macro_step, max_nuts_depth, max_error, *, seed=None,
+                 device=0, compat=True, chain_offset=0):
+    """walnuts.py:279-359: one transition; returns the next state vector(s)."""
+    cb, single = _pkg_batch(rng, theta, logp, grad, inv_mass, macro_step, max_nuts_depth, max_error,
+                            seed, device, compat, chain_offset)
+    with cb:
+        cb.run(1, draws=False, nevals=False)
+        out = cb.get_state()
+    return out[0] if single else out

@@ -1,0 +1,482 @@
+// C-ABI of the B200-native WALNUTS/NUTS sampler (include/walnuts_cuda.h).
+// Host side: handle management, kernel dispatch by (target, dimension), launch + timing.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/walnuts_cuda.h"
+#include "wn_package.cuh"
+#include "wn_walnutspy.cuh"
+
+using namespace wn;
+
+struct wn_handle {
+  wn_config cfg;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  double* d_state = nullptr;
+  bool have_state = false;
+  double2* d_scratch = nullptr;
+  size_t scratch_bytes = 0;
+  unsigned int* d_queue = nullptr;
+  unsigned long long* d_totals = nullptr;
+  double* d_p0 = nullptr;  // inv_var | X | y(T)
+  double* d_p1 = nullptr;  // y(N)
+  double* d_inv_mass = nullptr;
+  double* d_H = nullptr;
+  double* d_delta = nullptr;
+  int64_t n_p0 = 0, n_p1 = 0;
+  double tau = 1.0;
+  uint32_t iter_done = 0;
+  float last_ms = 0.f;
+  int64_t last_launches = 0;
+  unsigned long long last_tot[2] = {0, 0};
+  int num_sms = 148;
+  std::string err;
+};
+
+static int fail(wn_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  return code;
+}
+#define CUDA_TRY(h, expr)                                                                \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess)                                                               \
+      return fail(h, WN_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));      \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------
+// kernel dispatch
+// ------------------------------------------------------------------------------------------
+template <int G, int E2>
+using StdNormalT = DiagGaussT<G, E2, true>;
+template <int G, int E2>
+using DiagT = DiagGaussT<G, E2, false>;
+
+struct LaunchPlan {
+  const void* fn;
+  int G, E2, NT;
+  size_t smem;
+  bool package;
+};
+
+template <template <int, int> class T, int G, int E2, int NT>
+static LaunchPlan plan_wpy() {
+  LaunchPlan p;
+  p.fn = (const void*)walnutspy_kernel<T, G, E2, NT>;
+  p.G = G; p.E2 = E2; p.NT = NT;
+  p.smem = (size_t)(3 * 2 * E2 * NT + 2 * ((G + 31) / 32) * 4) * sizeof(double);
+  p.package = false;
+  return p;
+}
+template <template <int, int> class T, int G, int E2, int NT>
+static LaunchPlan plan_pkg() {
+  LaunchPlan p;
+  p.fn = (const void*)package_kernel<T, G, E2, NT>;
+  p.G = G; p.E2 = E2; p.NT = NT;
+  p.smem = (size_t)(2 * 2 * E2 * NT + 2 * ((G + 31) / 32) * 4) * sizeof(double);
+  p.package = true;
+  return p;
+}
+
+template <template <int, int> class T>
+static bool pick_generic(bool pkg, int d, LaunchPlan& p) {
+#define WN_PICK(G, E2, NT)                                              \
+  if (d <= 2 * (G) * (E2)) {                                            \
+    p = pkg ? plan_pkg<T, G, E2, NT>() : plan_wpy<T, G, E2, NT>();      \
+    return true;                                                        \
+  }
+  WN_PICK(1, 2, 128)
+  WN_PICK(1, 6, 128)
+  WN_PICK(4, 4, 128)
+  WN_PICK(16, 4, 128)
+  WN_PICK(32, 8, 128)
+  WN_PICK(128, 4, 128)
+  WN_PICK(256, 4, 256)
+#undef WN_PICK
+  return false;
+}
+template <template <int, int> class T>
+static bool pick_warp(bool pkg, int d, LaunchPlan& p) {  // targets that need the chain inside one warp
+#define WN_PICK(G, E2, NT)                                              \
+  if (d <= 2 * (G) * (E2)) {                                            \
+    p = pkg ? plan_pkg<T, G, E2, NT>() : plan_wpy<T, G, E2, NT>();      \
+    return true;                                                        \
+  }
+  WN_PICK(1, 6, 128)
+  WN_PICK(4, 4, 128)
+  WN_PICK(16, 4, 128)
+  WN_PICK(32, 8, 128)
+#undef WN_PICK
+  return false;
+}
+
+static bool pick_plan(const wn_config& c, LaunchPlan& p) {
+  const bool pkg = c.mode == WN_MODE_PACKAGE;
+  if (pkg) return false;  // TODO package kernel
+  switch (c.target) {
+    case WN_TARGET_STD_NORMAL: return pick_generic<StdNormalT>(pkg, c.d, p);
+    case WN_TARGET_DIAG_GAUSS: return pick_generic<DiagT>(pkg, c.d, p);
+    case WN_TARGET_FUNNEL: return pick_warp<FunnelT>(pkg, c.d, p);
+    case WN_TARGET_FUNNEL_PKG: return pick_warp<FunnelPkgT>(pkg, c.d, p);
+    case WN_TARGET_CORR_GAUSS:
+      if (c.d != 2) return false;
+      p = pkg ? plan_pkg<CorrGaussT, 1, 1, 128>() : plan_wpy<CorrGaussT, 1, 1, 128>();
+      return true;
+    default: return false;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// small utility kernels
+// ------------------------------------------------------------------------------------------
+__global__ void moments_kernel(const double* __restrict__ state, int n_chains, int d,
+                               double* __restrict__ mean, double* __restrict__ var) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= d) return;
+  double s = 0.0;
+  for (int c = 0; c < n_chains; ++c) s += state[(size_t)c * d + j];
+  const double m = s / n_chains;
+  double ss = 0.0;
+  for (int c = 0; c < n_chains; ++c) {
+    const double x = state[(size_t)c * d + j] - m;
+    ss = fma(x, x, ss);
+  }
+  mean[j] = m;
+  var[j] = n_chains > 1 ? ss / (n_chains - 1) : 0.0;
+}
+
+__global__ void fp64_fma_kernel(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6,
+         x7 = x0 + 7;
+  for (int i = 0; i < iters; ++i) {
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+// ------------------------------------------------------------------------------------------
+// C-ABI
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+int wn_abi_version(void) { return WN_ABI_VERSION; }
+
+int wn_target_id(const char* name) {
+  if (!name) return WN_EINVAL;
+  static const struct { const char* n; int id; } tab[] = {
+      {"std_normal", WN_TARGET_STD_NORMAL}, {"diag_gauss", WN_TARGET_DIAG_GAUSS},
+      {"funnel", WN_TARGET_FUNNEL},         {"logreg", WN_TARGET_LOGREG},
+      {"stock_watson", WN_TARGET_STOCK_WATSON}, {"corr_gauss", WN_TARGET_CORR_GAUSS},
+      {"funnel_pkg", WN_TARGET_FUNNEL_PKG}};
+  for (auto& e : tab)
+    if (!strcmp(e.n, name)) return e.id;
+  return WN_EINVAL;
+}
+
+const char* wn_last_error(const wn_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+int wn_create(const wn_config* cfg, wn_handle** out) {
+  if (!cfg || !out) return WN_EINVAL;
+  *out = nullptr;
+  wn_handle* h = new wn_handle();
+  h->cfg = *cfg;
+  *out = h;  // returned even on failure so that wn_last_error() can be read; caller destroys it
+  const wn_config& c = h->cfg;
+  // argument validation mirrors reference walnuts.py:309-320 (ValueError) and WALNUTS.py:140,146
+  if (c.d <= 0 || c.n_chains <= 0) return fail(h, WN_EINVAL, "d and n_chains must be positive");
+  if (!(c.H0 > 0)) return fail(h, WN_EINVAL, "non-positive macro_step");
+  if (!(c.M > 0) || c.M > 30) return fail(h, WN_EINVAL, "non-positive max_nuts_depth (or > 30)");
+  if (!(c.delta > 0)) return fail(h, WN_EINVAL, "non-positive max_error");
+  if (c.mode != WN_MODE_WALNUTSPY && c.mode != WN_MODE_PACKAGE) return fail(h, WN_EINVAL, "bad mode");
+  if (c.mode == WN_MODE_WALNUTSPY) {
+    if (c.integrator < WN_INT_FIXED || c.integrator > WN_INT_R2P) return fail(h, WN_EINVAL, "bad integrator");
+    if (c.minC < 0 || c.maxC < c.minC || c.maxC > 30) return fail(h, WN_EINVAL, "need 0 <= minC <= maxC <= 30");
+    if (!(c.jitter >= 0 && c.jitter < 1)) return fail(h, WN_EINVAL, "stepSizeRandScale must be in [0,1)");
+  }
+  if (c.dg < 0 || c.dg > c.d) return fail(h, WN_EINVAL, "dg must be in [0, d]");
+  LaunchPlan p;
+  if (!pick_plan(c, p)) return fail(h, WN_EUNSUPPORTED, "no CUDA kernel for this target/dimension");
+  CUDA_TRY(h, cudaSetDevice(c.device));
+  cudaDeviceProp prop;
+  CUDA_TRY(h, cudaGetDeviceProperties(&prop, c.device));
+  h->num_sms = prop.multiProcessorCount;
+  CUDA_TRY(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CUDA_TRY(h, cudaEventCreate(&h->ev0));
+  CUDA_TRY(h, cudaEventCreate(&h->ev1));
+  CUDA_TRY(h, cudaMalloc(&h->d_state, (size_t)c.n_chains * c.d * sizeof(double)));
+  CUDA_TRY(h, cudaMalloc(&h->d_queue, sizeof(unsigned int)));
+  CUDA_TRY(h, cudaMalloc(&h->d_totals, 2 * sizeof(unsigned long long)));
+  return WN_OK;
+}
+
+void wn_destroy(wn_handle* h) {
+  if (!h) return;
+  if (h->stream) {
+    cudaSetDevice(h->cfg.device);
+    cudaStreamSynchronize(h->stream);
+  }
+  cudaFree(h->d_state); cudaFree(h->d_scratch); cudaFree(h->d_queue); cudaFree(h->d_totals);
+  cudaFree(h->d_p0); cudaFree(h->d_p1); cudaFree(h->d_inv_mass); cudaFree(h->d_H); cudaFree(h->d_delta);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+static int upload(wn_handle* h, double** dst, const double* src, int64_t n, int on_device) {
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  if (*dst) { cudaFree(*dst); *dst = nullptr; }
+  CUDA_TRY(h, cudaMalloc(dst, (size_t)n * sizeof(double)));
+  CUDA_TRY(h, cudaMemcpyAsync(*dst, src, (size_t)n * sizeof(double),
+                              on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return WN_OK;
+}
+
+int wn_set_data(wn_handle* h, const char* key, const double* ptr, int64_t n, int on_device) {
+  if (!h || !key || !ptr || n <= 0) return fail(h, WN_EINVAL, "wn_set_data: bad argument");
+  const wn_config& c = h->cfg;
+  if (!strcmp(key, "inv_var")) {
+    if (n != c.d) return fail(h, WN_EINVAL, "inv_var must have d entries");
+    h->n_p0 = n;
+    return upload(h, &h->d_p0, ptr, n, on_device);
+  }
+  if (!strcmp(key, "inv_mass")) {
+    if (n != c.d) return fail(h, WN_EINVAL, "size mismatch between theta and inv_mass");
+    return upload(h, &h->d_inv_mass, ptr, n, on_device);
+  }
+  if (!strcmp(key, "H")) {
+    if (n != c.n_chains) return fail(h, WN_EINVAL, "H must have n_chains entries");
+    return upload(h, &h->d_H, ptr, n, on_device);
+  }
+  if (!strcmp(key, "delta")) {
+    if (n != c.n_chains) return fail(h, WN_EINVAL, "delta must have n_chains entries");
+    return upload(h, &h->d_delta, ptr, n, on_device);
+  }
+  if (!strcmp(key, "X")) { h->n_p0 = n; return upload(h, &h->d_p0, ptr, n, on_device); }
+  if (!strcmp(key, "y")) {
+    if (c.target == WN_TARGET_STOCK_WATSON) { h->n_p0 = n; return upload(h, &h->d_p0, ptr, n, on_device); }
+    h->n_p1 = n;
+    return upload(h, &h->d_p1, ptr, n, on_device);
+  }
+  if (!strcmp(key, "tau")) {
+    if (on_device) return fail(h, WN_EINVAL, "tau must be a host scalar");
+    h->tau = ptr[0];
+    return WN_OK;
+  }
+  return fail(h, WN_EINVAL, std::string("unknown data key ") + key);
+}
+
+int wn_set_state(wn_handle* h, const double* q, int on_device) {
+  if (!h || !q) return fail(h, WN_EINVAL, "wn_set_state: bad argument");
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  const size_t bytes = (size_t)h->cfg.n_chains * h->cfg.d * sizeof(double);
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_state, q, bytes,
+                              on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  h->have_state = true;
+  return WN_OK;
+}
+
+int wn_get_state(wn_handle* h, double* q, int on_device) {
+  if (!h || !q) return fail(h, WN_EINVAL, "wn_get_state: bad argument");
+  if (!h->have_state) return fail(h, WN_ESTATE, "no state set");
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  const size_t bytes = (size_t)h->cfg.n_chains * h->cfg.d * sizeof(double);
+  CUDA_TRY(h, cudaMemcpyAsync(q, h->d_state, bytes,
+                              on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return WN_OK;
+}
+
+int wn_run_async(wn_handle* h, int64_t n_iter, double* d_draws, double* d_diag, uint64_t* d_nevalF,
+                 uint64_t* d_nevalB) {
+  if (!h) return WN_EINVAL;
+  if (n_iter <= 0 || n_iter > 0x7fffffff) return fail(h, WN_EINVAL, "n_iter must be positive");
+  if (!h->have_state) return fail(h, WN_ESTATE, "wn_run before wn_set_state");
+  const wn_config& c = h->cfg;
+  if (c.target == WN_TARGET_DIAG_GAUSS && !h->d_p0) return fail(h, WN_ESTATE, "diag_gauss needs data key inv_var");
+  if (c.mode == WN_MODE_PACKAGE && !h->d_inv_mass) return fail(h, WN_ESTATE, "package mode needs data key inv_mass");
+  LaunchPlan p;
+  if (!pick_plan(c, p)) return fail(h, WN_EUNSUPPORTED, "no CUDA kernel for this target/dimension");
+  CUDA_TRY(h, cudaSetDevice(c.device));
+  CUDA_TRY(h, cudaFuncSetAttribute(p.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+  int occ = 0;
+  CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, p.fn, p.NT, p.smem));
+  if (occ < 1) return fail(h, WN_ECUDA, "kernel does not fit on an SM");
+  const int gpb = p.NT / p.G;
+  long long blocks = (long long)h->num_sms * occ;
+  const long long need = ((long long)c.n_chains + gpb - 1) / gpb;
+  if (blocks > need) blocks = need;
+  const int nslot = (int)blocks * gpb;
+  const int nvec = p.package ? package_scratch_vectors(c.M) : scratch_vectors(c.M);
+  const size_t sbytes = (size_t)nvec * p.E2 * nslot * p.G * sizeof(double2);
+  if (sbytes > h->scratch_bytes) {
+    if (h->d_scratch) cudaFree(h->d_scratch);
+    h->d_scratch = nullptr;
+    h->scratch_bytes = 0;
+    CUDA_TRY(h, cudaMalloc(&h->d_scratch, sbytes));
+    h->scratch_bytes = sbytes;
+  }
+  CUDA_TRY(h, cudaMemsetAsync(h->d_queue, 0, sizeof(unsigned int), h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(h->d_totals, 0, 2 * sizeof(unsigned long long), h->stream));
+
+  TargetParams tp;
+  tp.p0 = h->d_p0; tp.p1 = h->d_p1; tp.n0 = (int)h->n_p0; tp.n1 = (int)h->n_p1;
+  tp.c0 = 1.0 / (h->tau * h->tau);
+
+  CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
+  if (!p.package) {
+    RunParams P;
+    memset(&P, 0, sizeof(P));
+    P.n_chains = c.n_chains; P.d = c.d; P.dg = c.dg; P.M = c.M; P.kind = c.integrator;
+    P.minC = c.minC; P.maxC = c.maxC; P.n_iter = (int)n_iter; P.iter0 = h->iter_done + 1;
+    P.seed_lo = (uint32_t)(c.seed & 0xffffffffu); P.seed_hi = (uint32_t)(c.seed >> 32);
+    P.chain_offset = (uint32_t)c.chain_offset;
+    P.H0 = c.H0; P.delta0 = c.delta; P.jitter = c.jitter; P.p0 = c.r2p_prob0;
+    P.log_p0 = c.log_p0; P.log_1mp0 = c.log_1mp0;
+    P.Hstep = h->d_H; P.delta = h->d_delta; P.state = h->d_state; P.draws = d_draws; P.diag = d_diag;
+    P.nevalF = (unsigned long long*)d_nevalF; P.nevalB = (unsigned long long*)d_nevalB;
+    P.totals = h->d_totals; P.scratch = h->d_scratch; P.nslot = nslot; P.queue = h->d_queue; P.tp = tp;
+    void* args[] = {&P};
+    CUDA_TRY(h, cudaLaunchKernel(p.fn, dim3((unsigned)blocks), dim3(p.NT), args, p.smem, h->stream));
+  } else {
+    PkgParams P;
+    memset(&P, 0, sizeof(P));
+    P.n_chains = c.n_chains; P.d = c.d; P.dg = c.dg; P.max_depth = c.M; P.compat = c.compat;
+    P.n_iter = (int)n_iter; P.iter0 = h->iter_done + 1;
+    P.seed_lo = (uint32_t)(c.seed & 0xffffffffu); P.seed_hi = (uint32_t)(c.seed >> 32);
+    P.chain_offset = (uint32_t)c.chain_offset;
+    P.macro_step = c.H0; P.max_error = c.delta; P.inv_mass = h->d_inv_mass;
+    P.state = h->d_state; P.draws = d_draws;
+    P.neval = (unsigned long long*)d_nevalF; P.totals = h->d_totals;
+    P.scratch = h->d_scratch; P.nslot = nslot; P.queue = h->d_queue; P.tp = tp;
+    void* args[] = {&P};
+    CUDA_TRY(h, cudaLaunchKernel(p.fn, dim3((unsigned)blocks), dim3(p.NT), args, p.smem, h->stream));
+  }
+  CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
+  h->iter_done += (uint32_t)n_iter;
+  h->last_launches = 1;
+  return WN_OK;
+}
+
+int wn_sync(wn_handle* h) {
+  if (!h) return WN_EINVAL;
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  CUDA_TRY(h, cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+  CUDA_TRY(h, cudaMemcpy(h->last_tot, h->d_totals, sizeof(h->last_tot), cudaMemcpyDeviceToHost));
+  return WN_OK;
+}
+
+int wn_run(wn_handle* h, int64_t n_iter, double* draws, double* diag, uint64_t* nevalF, uint64_t* nevalB,
+           int on_device) {
+  if (!h) return WN_EINVAL;
+  if (on_device) {
+    int rc = wn_run_async(h, n_iter, draws, diag, nevalF, nevalB);
+    if (rc) return rc;
+    return wn_sync(h);
+  }
+  if (n_iter <= 0 || n_iter > 0x7fffffff) return fail(h, WN_EINVAL, "n_iter must be positive");
+  const wn_config& c = h->cfg;
+  CUDA_TRY(h, cudaSetDevice(c.device));
+  const size_t nd = draws ? (size_t)n_iter * c.n_chains * c.dg : 0;
+  const size_t ng = diag ? (size_t)n_iter * c.n_chains * WN_DIAG_COLS : 0;
+  double *dd = nullptr, *dgp = nullptr;
+  uint64_t *df = nullptr, *db = nullptr;
+  int rc = WN_OK;
+  auto cleanup = [&]() { cudaFree(dd); cudaFree(dgp); cudaFree(df); cudaFree(db); };
+#define TRY_OR_CLEAN(expr)                                                              \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      cleanup();                                                                        \
+      return fail(h, WN_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));     \
+    }                                                                                   \
+  } while (0)
+  if (nd) TRY_OR_CLEAN(cudaMalloc(&dd, nd * sizeof(double)));
+  if (ng) TRY_OR_CLEAN(cudaMalloc(&dgp, ng * sizeof(double)));
+  if (nevalF) TRY_OR_CLEAN(cudaMalloc(&df, (size_t)c.n_chains * sizeof(uint64_t)));
+  if (nevalB) TRY_OR_CLEAN(cudaMalloc(&db, (size_t)c.n_chains * sizeof(uint64_t)));
+  if (db) TRY_OR_CLEAN(cudaMemsetAsync(db, 0, (size_t)c.n_chains * sizeof(uint64_t), h->stream));
+  rc = wn_run_async(h, n_iter, dd, dgp, df, db);
+  if (rc == WN_OK) rc = wn_sync(h);
+  if (rc != WN_OK) { cleanup(); return rc; }
+  if (nd) TRY_OR_CLEAN(cudaMemcpy(draws, dd, nd * sizeof(double), cudaMemcpyDeviceToHost));
+  if (ng) TRY_OR_CLEAN(cudaMemcpy(diag, dgp, ng * sizeof(double), cudaMemcpyDeviceToHost));
+  if (nevalF) TRY_OR_CLEAN(cudaMemcpy(nevalF, df, (size_t)c.n_chains * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  if (nevalB) TRY_OR_CLEAN(cudaMemcpy(nevalB, db, (size_t)c.n_chains * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  cleanup();
+#undef TRY_OR_CLEAN
+  return WN_OK;
+}
+
+int wn_last_kernel_ms(wn_handle* h, float* ms) {
+  if (!h || !ms) return WN_EINVAL;
+  *ms = h->last_ms;
+  return WN_OK;
+}
+int wn_last_launches(wn_handle* h, int64_t* n) {
+  if (!h || !n) return WN_EINVAL;
+  *n = h->last_launches;
+  return WN_OK;
+}
+int wn_last_grad_evals(wn_handle* h, uint64_t* forward, uint64_t* backward) {
+  if (!h) return WN_EINVAL;
+  if (forward) *forward = h->last_tot[0];
+  if (backward) *backward = h->last_tot[1];
+  return WN_OK;
+}
+
+int wn_moments(wn_handle* h, double* mean, double* var) {
+  if (!h || !mean || !var) return fail(h, WN_EINVAL, "wn_moments: bad argument");
+  if (!h->have_state) return fail(h, WN_ESTATE, "no state set");
+  const wn_config& c = h->cfg;
+  CUDA_TRY(h, cudaSetDevice(c.device));
+  double* buf = nullptr;
+  CUDA_TRY(h, cudaMalloc(&buf, 2 * (size_t)c.d * sizeof(double)));
+  moments_kernel<<<(c.d + 127) / 128, 128, 0, h->stream>>>(h->d_state, c.n_chains, c.d, buf, buf + c.d);
+  cudaError_t e = cudaMemcpyAsync(mean, buf, c.d * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(var, buf + c.d, c.d * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(buf);
+  if (e != cudaSuccess) return fail(h, WN_ECUDA, cudaGetErrorString(e));
+  return WN_OK;
+}
+
+void* wn_stream(wn_handle* h) { return h ? (void*)h->stream : nullptr; }
+
+int wn_fp64_peak(int device, double* flops_per_s) {
+  if (!flops_per_s) return WN_EINVAL;
+  if (cudaSetDevice(device) != cudaSuccess) return WN_ECUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return WN_ECUDA;
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 16;
+  double* out = nullptr;
+  if (cudaMalloc(&out, (size_t)blocks * threads * sizeof(double)) != cudaSuccess) return WN_ENOMEM;
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(a);
+    fp64_fma_kernel<<<blocks, threads>>>(out, iters, 0.999999, 1e-7);
+    cudaEventRecord(b);
+    if (cudaEventSynchronize(b) != cudaSuccess) { cudaFree(out); return WN_ECUDA; }
+    float ms;
+    cudaEventElapsedTime(&ms, a, b);
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  cudaFree(out);
+  *flops_per_s = 2.0 * 8.0 * (double)iters * blocks * threads / (best * 1e-3);
+  return WN_OK;
+}
+
+}  // extern "C"

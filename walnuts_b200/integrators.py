@@ -1,0 +1,39 @@
+"""Macro-step integrator handles, mirroring reference WALNUTSpy/adaptiveIntegrators.py.
+
+The reference passes Python functions `integrator(q, v, g, Ham0, h, xi, lpFun, delta, auxPar)`
+(adaptiveIntegrators.py:49,65,361); here the same names are registry handles selecting the CUDA
+implementation inside the persistent kernel (walnuts_b200/csrc/wn_walnutspy.cuh).
+"""
+
+
+class _Integrator:
+    def __init__(self, name, kind, ref):
+        self.name, self.kind, self.ref = name, kind, ref
+
+    def __repr__(self):
+        return f"<walnuts_b200 integrator {self.name} ({self.ref})>"
+
+    def __call__(self, *a, **k):
+        raise TypeError(f"{self.name} is a handle for the CUDA integrator; it runs inside "
+                        "walnuts_b200.WALNUTS(...) and cannot be called on host arrays")
+
+
+fixedLeapFrog = _Integrator("fixedLeapFrog", 0, "adaptiveIntegrators.py:49-59")
+adaptLeapFrogD = _Integrator("adaptLeapFrogD", 1, "adaptiveIntegrators.py:65-137")
+adaptLeapFrogR2P = _Integrator("adaptLeapFrogR2P", 2, "adaptiveIntegrators.py:361-475")
+
+
+class integratorAuxPar:
+    """adaptiveIntegrators.integratorAuxPar (adaptiveIntegrators.py:36-44); the fields of the
+    integrators that are not on the hot path (maxFPiter, FPtol, FPNewton, rescaledGradThresh) are
+    accepted and ignored."""
+
+    def __init__(self, minC=0, maxC=10, R2Pprob0=2.0 / 3.0, maxFPiter=30, FPtol=1.0e-8, FPNewton=False,
+                 rescaledGradThresh=5.0):
+        self.minC = minC
+        self.maxC = maxC
+        self.R2Pprob0 = R2Pprob0
+        self.maxFPiter = maxFPiter
+        self.FPtol = FPtol
+        self.FPNewton = FPNewton
+        self.rescaledGradThresh = rescaledGradThresh

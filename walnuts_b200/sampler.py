@@ -1,0 +1,165 @@
+"""Low-level host wrapper over the C-ABI: one `ChainBatch` = one handle = the chains of one GPU.
+
+numpy arrays are the default I/O; torch CUDA tensors are accepted as optional device-resident I/O
+(their data pointers are passed straight through; torch is not imported unless one is given).
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import WalnutsError
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+def _ptr(x):
+    if x is None:
+        return None, 0
+    if _is_torch(x):
+        if not x.is_cuda or not x.is_contiguous():
+            raise WalnutsError("torch tensors passed to walnuts_b200 must be contiguous CUDA tensors")
+        return C.c_void_p(x.data_ptr()), 1
+    return C.c_void_p(x.ctypes.data), 0
+
+
+class ChainBatch:
+    """All chains of one device.  Mirrors wn_create / wn_set_data / wn_set_state / wn_run."""
+
+    def __init__(self, target, d, n_chains, mode="walnutspy", integrator="fixed", H0=0.2, jitter=0.2,
+                 delta=0.05, M=10, minC=0, maxC=10, r2p_prob0=2.0 / 3.0, seed=0, chain_offset=0,
+                 device=0, dg=None, compat=True, data=None):
+        self._lib = _ffi.load()
+        self._h = C.c_void_p()
+        cfg = _ffi.WnConfig()
+        cfg.target = _ffi.TARGETS[target] if isinstance(target, str) else int(target)
+        cfg.mode = {"walnutspy": _ffi.MODE_WALNUTSPY, "package": _ffi.MODE_PACKAGE}[mode]
+        cfg.integrator = {"fixed": 0, "D": 1, "R2P": 2}[integrator] if isinstance(integrator, str) else int(integrator)
+        cfg.d, cfg.n_chains, cfg.device = int(d), int(n_chains), int(device)
+        cfg.dg = int(d if dg is None else dg)
+        cfg.M, cfg.minC, cfg.maxC = int(M), int(minC), int(maxC)
+        cfg.compat = int(bool(compat))
+        cfg.H0, cfg.jitter, cfg.delta = float(H0), float(jitter), float(delta)
+        cfg.r2p_prob0 = float(r2p_prob0)
+        # logs computed by the host libm exactly as the reference does (adaptiveIntegrators.py:433,437)
+        cfg.log_p0 = float(np.log(r2p_prob0)) if 0 < r2p_prob0 else -math.inf
+        cfg.log_1mp0 = float(np.log(1.0 - r2p_prob0)) if r2p_prob0 < 1 else -math.inf
+        cfg.seed, cfg.chain_offset = int(seed), int(chain_offset)
+        self.cfg = cfg
+        self.d, self.n_chains, self.dg = cfg.d, cfg.n_chains, cfg.dg
+        rc = self._lib.wn_create(C.byref(cfg), C.byref(self._h))
+        if rc != 0:
+            msg = self._err()
+            self.close()
+            if rc == -1:
+                raise ValueError(msg)       # the reference raises ValueError (walnuts.py:309-320)
+            raise WalnutsError(f"wn_create: {_ffi.ERRORS.get(rc, rc)}: {msg}")
+        for k, val in (data or {}).items():
+            self.set_data(k, val)
+
+    # -- plumbing ---------------------------------------------------------------------------
+    def _err(self):
+        return self._lib.wn_last_error(self._h).decode() if self._h else "no handle"
+
+    def _check(self, rc, what):
+        if rc != 0:
+            msg = self._err()
+            if rc == -1:
+                raise ValueError(f"{what}: {msg}")
+            raise WalnutsError(f"{what}: {_ffi.ERRORS.get(rc, rc)}: {msg}")
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.wn_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- data / state -----------------------------------------------------------------------
+    def set_data(self, key, arr):
+        if not _is_torch(arr):
+            arr = np.ascontiguousarray(arr, dtype=np.float64)
+            n = arr.size
+        else:
+            n = arr.numel()
+        p, dev = _ptr(arr)
+        self._check(self._lib.wn_set_data(self._h, key.encode(), p, n, dev), f"wn_set_data({key})")
+
+    def set_state(self, q):
+        if not _is_torch(q):
+            q = np.ascontiguousarray(np.broadcast_to(np.asarray(q, dtype=np.float64), (self.n_chains, self.d)))
+        p, dev = _ptr(q)
+        self._check(self._lib.wn_set_state(self._h, p, dev), "wn_set_state")
+
+    def get_state(self, out=None):
+        if out is None:
+            out = np.empty((self.n_chains, self.d))
+        p, dev = _ptr(out)
+        self._check(self._lib.wn_get_state(self._h, p, dev), "wn_get_state")
+        return out
+
+    # -- sampling ---------------------------------------------------------------------------
+    def run(self, n_iter, draws=True, diag=False, nevals=True):
+        """Host-buffer path (H2D/D2H inside): returns dict(draws, diag, nevalF, nevalB)."""
+        n_iter = int(n_iter)
+        out = {}
+        d_arr = np.empty((n_iter, self.n_chains, self.dg)) if draws and self.dg > 0 else None
+        g_arr = np.empty((n_iter, self.n_chains, _ffi.DIAG_COLS)) if diag else None
+        f_arr = np.zeros(self.n_chains, dtype=np.uint64) if nevals else None
+        b_arr = np.zeros(self.n_chains, dtype=np.uint64) if nevals else None
+        rc = self._lib.wn_run(self._h, n_iter, _ptr(d_arr)[0], _ptr(g_arr)[0], _ptr(f_arr)[0], _ptr(b_arr)[0], 0)
+        self._check(rc, "wn_run")
+        out.update(draws=d_arr, diag=g_arr, nevalF=f_arr, nevalB=b_arr)
+        return out
+
+    def run_device(self, n_iter, draws=None, diag=None, nevalF=None, nevalB=None, sync=True):
+        """Device-buffer path: torch CUDA tensors (or None) are filled in place."""
+        ptrs = [_ptr(x)[0] for x in (draws, diag, nevalF, nevalB)]
+        self._check(self._lib.wn_run_async(self._h, int(n_iter), *ptrs), "wn_run_async")
+        if sync:
+            self.sync()
+
+    def sync(self):
+        self._check(self._lib.wn_sync(self._h), "wn_sync")
+
+    def last_kernel_ms(self):
+        ms = C.c_float()
+        self._check(self._lib.wn_last_kernel_ms(self._h, C.byref(ms)), "wn_last_kernel_ms")
+        return float(ms.value)
+
+    def last_launches(self):
+        n = C.c_int64()
+        self._check(self._lib.wn_last_launches(self._h, C.byref(n)), "wn_last_launches")
+        return int(n.value)
+
+    def last_grad_evals(self):
+        f, b = C.c_uint64(), C.c_uint64()
+        self._check(self._lib.wn_last_grad_evals(self._h, C.byref(f), C.byref(b)), "wn_last_grad_evals")
+        return int(f.value), int(b.value)
+
+    def moments(self):
+        mean, var = np.empty(self.d), np.empty(self.d)
+        self._check(self._lib.wn_moments(self._h, _ptr(mean)[0], _ptr(var)[0]), "wn_moments")
+        return mean, var
+
+    @property
+    def stream(self):
+        return self._lib.wn_stream(self._h)
+
+
+def fp64_peak(device=0):
+    lib = _ffi.load()
+    v = C.c_double()
+    rc = lib.wn_fp64_peak(int(device), C.byref(v))
+    if rc != 0:
+        raise WalnutsError(f"wn_fp64_peak: {_ffi.ERRORS.get(rc, rc)}")
+    return float(v.value)
