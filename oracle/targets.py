@@ -8,7 +8,6 @@ Targets that exist in the reference are restated with the reference's own operat
 order; the three the reference lacks (diag Gaussian, logistic regression, Stock-Watson)
 are defined here and are the specification for the CUDA targets (SURVEY.md rows T2,T4,T5).
 """
-import json
 import os
 
 import numpy as np
@@ -91,13 +90,12 @@ def synth_logreg_data(N=100_000, P=100, seed=0):
 
 
 def load_sw_data(path=None):
-    """The T=252 series of reference WALNUTSpy_examples/StockWatson/swdata.json.  The values are
-    data, not code; a copy of the 252 numbers lives in tests/golden/swdata.json so that the GPU
-    box (which has no /root/reference) can run the Stock-Watson target."""
+    """The T=252 observations `y` of the reference's Stock-Watson example
+    (WALNUTSpy_examples/StockWatson/swdata.json), stored as a plain array in tests/golden/sw_y.npy so
+    that the GPU box (which has no /root/reference) can run the Stock-Watson target.  Data, not code."""
     if path is None:
-        path = os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "swdata.json")
-    with open(path) as f:
-        return np.asarray(json.load(f)["y"], dtype=np.float64)
+        path = os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "sw_y.npy")
+    return np.load(path)
 
 
 def make_stock_watson(y):

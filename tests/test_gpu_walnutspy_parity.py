@@ -165,3 +165,44 @@ def test_many_chains_independent_of_scheduling(cuda_lib):
             cb.set_state(q0[c:c + 1])
             one = cb.run(3)["draws"]
         assert np.array_equal(one[:, 0], big[:, c])
+
+
+import glob
+import json
+import os
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "wpy_*.npz"))), ids=os.path.basename)
+def test_walnutspy_golden_from_real_reference(cuda_lib, path):
+    """CUDA vs the REAL reference's stored outputs (tests/golden/make_golden.py), through the drop-in
+    WALNUTS(...) surface.  Funnel cases are compared per transition on identical inputs (chaotic
+    dynamics amplify 1-ulp differences across transitions, see test_funnel10); the others free-running."""
+    import walnuts_b200 as wb
+    z = np.load(path)
+    m = json.loads(str(z["meta"]))
+    tg = {"std_normal": wb.targets.stdGauss, "funnel": wb.targets.funnel10, "corr_gauss": wb.targets.corrGauss}[m["target"]]
+    ig = {"fixed": wb.fixedLeapFrog, "D": wb.adaptLeapFrogD, "R2P": wb.adaptLeapFrogR2P}[m["integrator"]]
+    aux = wb.integratorAuxPar(minC=m["minC"], maxC=m["maxC"])
+    ref_s, ref_d = z["samples"], z["diagnostics"]
+    kw = dict(integrator=ig, H0=m["H0"], delta0=m["delta"], warmupIter=0, M=m["M"], igrAux=aux, adaptH=False,
+              adaptDelta=False, seed=m["seed"], chain_offset=m["chain"])
+    if m["target"] != "funnel":
+        s, d = wb.WALNUTS(tg, z["q0"], numIter=m["n_iter"], **kw)
+        assert s.shape == ref_s.shape and d.shape == ref_d.shape
+        ok, err = close(s, ref_s)
+        assert ok, f"max rel err {err:.3e}"
+        assert np.array_equal(d[:, EXACT_COLS], ref_d[:, EXACT_COLS])
+        ok, err = close(d[:, FLOAT_COLS], ref_d[:, FLOAT_COLS], rtol=1e-9)
+        assert ok, err
+    else:
+        from walnuts_b200 import ChainBatch
+        with ChainBatch("funnel", 11, 1, integrator=m["integrator"], H0=m["H0"], delta=m["delta"], M=m["M"],
+                        minC=m["minC"], maxC=m["maxC"], seed=m["seed"], chain_offset=m["chain"]) as cb:
+            for it in range(m["n_iter"]):
+                cb.set_state(ref_s[:, it][None, :])
+                out = cb.run(1, draws=True, diag=True)
+                ok, err = close(out["draws"][0, 0], ref_s[:, it + 1])
+                assert ok, f"transition {it}: max rel err {err:.3e}"
+                assert np.array_equal(out["diag"][0, 0][EXACT_COLS], ref_d[it][EXACT_COLS])

@@ -1,0 +1,88 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every declared symbol, argument
+validation mirrors the reference's error behaviour (no compute calls; no GPU needed), diagnostics."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_abi_exports_every_declared_symbol(cuda_lib):
+    from walnuts_b200 import _ffi
+    hdr = open(os.path.join(ROOT, "include", "walnuts_cuda.h")).read()
+    declared = set(re.findall(r"\b(wn_[a-z0-9_]+)\s*\(", hdr)) - {"wn_handle", "wn_config"}
+    assert declared == set(_ffi.SYMBOLS), declared ^ set(_ffi.SYMBOLS)
+    for s in declared:
+        assert hasattr(cuda_lib, s)
+    assert cuda_lib.wn_abi_version() == 1
+    assert cuda_lib.wn_target_id(b"funnel") == 2 and cuda_lib.wn_target_id(b"nope") < 0
+
+
+def test_config_struct_layout_matches_header(cuda_lib):
+    from walnuts_b200 import _ffi
+    assert C.sizeof(_ffi.WnConfig) == 12 * 4 + 6 * 8 + 2 * 8
+
+
+def test_create_validation_without_gpu(cuda_lib):
+    """wn_create validates before touching CUDA: the reference's ValueError cases (walnuts.py:309-320)."""
+    from walnuts_b200 import ChainBatch
+    for kw in (dict(H0=0.0), dict(M=0), dict(delta=-1.0), dict(minC=3, maxC=2), dict(jitter=1.5)):
+        args = dict(target="std_normal", d=3, n_chains=2, H0=0.5, M=5, delta=0.1)
+        args.update(kw)
+        with pytest.raises(ValueError):
+            ChainBatch(**args)
+
+
+def test_python_callables_are_rejected_loudly(cuda_lib):
+    import walnuts_b200 as wb
+    with pytest.raises(TypeError, match="no CPU fallback"):
+        wb.WALNUTS(lambda q: [0.0, -q], np.zeros(3), numIter=1, warmupIter=0)
+    with pytest.raises(TypeError):
+        wb.targets.stdGauss(np.zeros(3))
+    with pytest.raises(NotImplementedError):
+        wb.WALNUTS(wb.targets.stdGauss, np.zeros(3), numIter=1, warmupIter=10)
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from walnuts_b200 import _ffi, build
+    monkeypatch.setattr(_ffi, "_lib", None)
+    monkeypatch.setattr(build, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_ffi.WalnutsError, match="no CPU fallback"):
+        _ffi.load()
+
+
+def test_product_does_not_import_oracle():
+    """The product package must never route through the oracle (checked textually)."""
+    pkg = os.path.join(ROOT, "walnuts_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, re.M), f
+                assert "/root/reference" not in txt, f
+
+
+def test_ess_estimator():
+    from walnuts_b200 import diagnostics as dg
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((64, 200))
+    ess, rhat = dg.ess_bulk(x)
+    assert 0.8 * x.size < ess < 1.25 * x.size and abs(rhat - 1) < 0.01
+    phi = 0.7
+    y = np.zeros((64, 400))
+    e = rng.standard_normal((64, 400))
+    y[:, 0] = e[:, 0] / np.sqrt(1 - phi ** 2)
+    for t in range(1, 400):
+        y[:, t] = phi * y[:, t - 1] + e[:, t]
+    ess, _ = dg.ess_bulk(y)
+    expect = y.size * (1 - phi) / (1 + phi)
+    assert 0.85 * expect < ess < 1.15 * expect
+    # sufficient statistics are additive across shards (multi-GPU reduction)
+    a, b = dg.chain_stats(y[:32], 40), dg.chain_stats(y[32:], 40)
+    tot = {k: a[k] + b[k] for k in ("m", "sum_mean", "sum_mean2", "sum_var", "acov_sum")}
+    tot["n"] = a["n"]
+    whole = dg.ess_from_stats(dg.chain_stats(y, 40))
+    assert np.isclose(dg.ess_from_stats(tot)[0], whole[0], rtol=1e-12)

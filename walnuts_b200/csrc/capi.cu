@@ -63,10 +63,10 @@ struct LaunchPlan {
   bool package;
 };
 
-template <template <int, int> class T, int G, int E2, int NT>
+template <template <int, int> class T, int G, int E2, int NT, int MINB = 1>
 static LaunchPlan plan_wpy() {
   LaunchPlan p;
-  p.fn = (const void*)walnutspy_kernel<T, G, E2, NT>;
+  p.fn = (const void*)walnutspy_kernel<T, G, E2, NT, MINB>;
   p.G = G; p.E2 = E2; p.NT = NT;
   p.smem = (size_t)(3 * 2 * E2 * NT + 2 * ((G + 31) / 32) * 4) * sizeof(double);
   p.package = false;
@@ -77,7 +77,7 @@ static LaunchPlan plan_pkg() {
   LaunchPlan p;
   p.fn = (const void*)package_kernel<T, G, E2, NT>;
   p.G = G; p.E2 = E2; p.NT = NT;
-  p.smem = (size_t)(2 * 2 * E2 * NT + 2 * ((G + 31) / 32) * 4) * sizeof(double);
+  p.smem = (size_t)(3 * 2 * E2 * NT + 2 * ((G + 31) / 32) * 4) * sizeof(double);
   p.package = true;
   return p;
 }
@@ -94,7 +94,7 @@ static bool pick_generic(bool pkg, int d, LaunchPlan& p) {
   WN_PICK(4, 4, 128)
   WN_PICK(16, 4, 128)
   WN_PICK(32, 8, 128)
-  WN_PICK(128, 4, 128)
+  WN_PICK(64, 8, 64)
   WN_PICK(256, 4, 256)
 #undef WN_PICK
   return false;
@@ -116,10 +116,19 @@ static bool pick_warp(bool pkg, int d, LaunchPlan& p) {  // targets that need th
 
 static bool pick_plan(const wn_config& c, LaunchPlan& p) {
   const bool pkg = c.mode == WN_MODE_PACKAGE;
-  if (pkg) return false;  // TODO package kernel
   switch (c.target) {
     case WN_TARGET_STD_NORMAL: return pick_generic<StdNormalT>(pkg, c.d, p);
-    case WN_TARGET_DIAG_GAUSS: return pick_generic<DiagT>(pkg, c.d, p);
+    case WN_TARGET_DIAG_GAUSS: {
+      const char* v = getenv("WN_VARIANT");   // tuning experiments only
+      if (v && !pkg && c.d > 512 && c.d <= 1024) {
+        switch (atoi(v)) {
+          case 1: p = plan_wpy<DiagT, 128, 4, 128, 3>(); return true;
+          case 2: p = plan_wpy<DiagT, 128, 4, 128, 4>(); return true;
+          default: break;
+        }
+      }
+      return pick_generic<DiagT>(pkg, c.d, p);
+    }
     case WN_TARGET_FUNNEL: return pick_warp<FunnelT>(pkg, c.d, p);
     case WN_TARGET_FUNNEL_PKG: return pick_warp<FunnelPkgT>(pkg, c.d, p);
     case WN_TARGET_CORR_GAUSS:

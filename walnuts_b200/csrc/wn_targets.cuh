@@ -40,14 +40,15 @@ struct DiagGaussT {
     }
   }
   __device__ __forceinline__ double lp_grad(const double (&q)[E], double (&g)[E], double*, int&) const {
-    double acc = 0.0;
+    double acc0 = 0.0, acc1 = 0.0;   // two partial sums: halves the dependent-FMA chain
 #pragma unroll
     for (int e = 0; e < E; ++e) {
       if constexpr (UNIT) g[e] = -q[e];
       else g[e] = -(q[e] * s[e]);
-      acc = fma(q[e], g[e], acc);
+      if (e & 1) acc1 = fma(q[e], g[e], acc1);
+      else acc0 = fma(q[e], g[e], acc0);
     }
-    return 0.5 * acc;
+    return 0.5 * (acc0 + acc1);
   }
 };
 

@@ -2,16 +2,18 @@
 // driver + WALNUTSpy/adaptiveIntegrators.py:49-137,361-475 macro steps).
 //
 // One group of G threads owns one chain at a time and keeps (q, v, g) of the active orbit end in
-// registers for the whole transition.  The kernel is ONE flat loop whose body is a single leapfrog
+// registers for the whole transition.  The kernel is ONE flat loop whose body is a leapfrog
 // micro-step; everything else (step-size search bookkeeping, tree logic, state selection, momentum
 // refresh, output) is a small state machine entered only when a pass of 2^c micro-steps ends.  So
 // chains that sit at different tree depths / different c never serialise each other's hot loop --
 // the SIMT analogue of "lock-free" chains.  Groups pull chains from a global queue.
 //
 // Per-chain memory outside registers:
-//   shared : checkpoint of the macro-step start state S, later the accepted out state O (3 vectors)
-//   global : slot-indexed scratch (other orbit end, two proposal slots, left-end stack of <= M
-//            pending dyadic levels) -- indexed by resident slot, not by chain, so it stays L2-sized.
+//   registers : q, v, g of the working state, target constants, 6 hot scalars
+//   shared    : checkpoint of the macro-step start state S, later the accepted out state O (3 vectors);
+//               the cold control block `Ctl` (one copy per warp; per-thread local copy when G < 32)
+//   global    : slot-indexed scratch (other orbit end, two proposal slots, left-end stack of <= M
+//               pending dyadic levels) -- indexed by resident slot, not by chain, so it stays L2-sized.
 #pragma once
 #include "wn_common.cuh"
 #include "wn_targets.cuh"
@@ -50,8 +52,25 @@ __host__ __device__ inline int scratch_vectors(int M) { return V_STACK + 2 * (M 
 #define WN_LOG_ZERO (-700.0)
 #define WN_WT_SUM_THRESH 0x1.78694fe9f73ccp-1009 /* numpy exp(-699) = 2.680137958338607e-304, reference constants.py:14 */
 
-template <template <int, int> class TargetTT, int G, int E2, int NT>
-__global__ void __launch_bounds__(NT) walnutspy_kernel(const __grid_constant__ RunParams P) {
+// Cold per-chain control state.  Every thread of a group computes identical values, so a copy may be
+// shared by the lanes of one warp (all lanes store the same value, then load it back).  Keeping it
+// out of registers leaves the register file to the FP64 working set of the hot loop.
+struct Ctl {
+  uint32_t chain, iter, nseq, dirbits;
+  int it, level, side, phase, c, If, Ib, cSim, maxTry;
+  uint32_t nleaf, n_new;
+  int maxInt0, maxInt1, L_, Lold, NdS, NdC, stopCode, propCur;
+  int bothPassive, candValid, forced, wIntact, sHnan;
+  int sN, sMinIf, sMaxIf, sMinC, sMaxC, sNne, sNz;
+  double Hbig, delta, jlo, jhi, xi, h, h2, Ham0, Hfwd, H0, lwtf, lwt;
+  double endH0, endH1, lwtSum0, lwtSum1, timeLen0, timeLen1;
+  double WoldSum, WnewSum, indexStat, indexStatOld, orbitLen, orbitLenSam;
+  double sMinL, sMaxL, sHmax, sHmin;
+  unsigned long long nF, nB, chainF, chainB;
+};
+
+template <template <int, int> class TargetTT, int G, int E2, int NT, int MINB = 1>
+__global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_constant__ RunParams P) {
   constexpr int E = 2 * E2;
   constexpr int GPB = NT / G;  // groups per block
   static_assert(NT % G == 0 && (G <= 32 || NT == G), "block must hold whole groups");
@@ -62,62 +81,41 @@ __global__ void __launch_bounds__(NT) walnutspy_kernel(const __grid_constant__ R
   double* ck = smem;                       // checkpoint: [3*E][NT]
   double* red = smem + 3 * E * NT;         // reduction scratch (G > 32)
   __shared__ uint32_t sh_bcast;
+  __shared__ Ctl sh_ctl[(G >= 32) ? NT / 32 : 1];
+  Ctl loc_ctl;                             // used only when several chains share a warp (G < 32)
+  volatile Ctl& C = (G >= 32) ? sh_ctl[threadIdx.x >> 5] : loc_ctl;
 
   const int tid = threadIdx.x;
   const int t = tid % G;
-  const int slot = blockIdx.x * GPB + tid / G;
   int parity = 0;
 
   // scratch addressing: vector vi, pair e2 -> scratch[((vi*E2 + e2) * nslot + slot) * G + t]
-  const size_t sc_stride = (size_t)P.nslot * G;
-  const size_t sc_off = (size_t)slot * G + t;
-  auto sc = [&](int vi, int e2) -> double2* { return P.scratch + ((size_t)(vi * E2 + e2)) * sc_stride + sc_off; };
+  auto sc = [&](int vi, int e2) -> double2* {
+    const size_t slot = (size_t)blockIdx.x * GPB + tid / G;
+    return P.scratch + ((size_t)(vi * E2 + e2) * P.nslot + slot) * G + t;
+  };
 
   Target target;
   target.init(P.tp, P.d, t);
 
-  // ---- register-resident state of the active end / working state -----------------------
+  // ---- register-resident working state -----------------------------------------------------
   double q[E], v[E], g[E];
-  // ---- per-chain control scalars (uniform across the group) ----------------------------
-  RngKey key;
-  key.k0 = P.seed_lo;
-  key.k1 = P.seed_hi;
-  key.chain = 0;
-  key.iter = 0;
-  uint32_t nseq = 0;
-  int chain = -1, it = 0;
-  double Hbig = 0, delta = 0, jlo = 0, jhi = 0;
-  uint32_t dirbits = 0;
-  int level = 0, side = -1;
-  uint32_t nleaf = 0, n_new = 0;
-  double xi = 1.0;
-  double h = 0, h2 = 0;
-  int phase = PH_FWD, c = 0, If = 0, Ib = 0, cSim = 0, maxTry = 0;
+  // ---- hot scalars --------------------------------------------------------------------------
   uint32_t steps_left = 0;
-  double hh = 0, ha = 0;
-  double Ham0 = 0, Hfwd = 0, H0 = 0, lwtf = 0, lwt = 0;
-  // two-element per-side state kept as scalar pairs (index 0 = forward end, 1 = backward end);
-  // dynamic indexing would push them to local memory
-  double endH0 = 0, endH1 = 0, lwtSum0 = 0, lwtSum1 = 0, timeLen0 = 0, timeLen1 = 0;
-  int maxInt0 = 0, maxInt1 = 0;
-  double WoldSum = 1.0, WnewSum = 0.0;
-  int L_ = 0, Lold = 0;
-  double indexStat = 0, indexStatOld = 0, orbitLen = 0, orbitLenSam = 0;
-  unsigned long long nF = 0, nB = 0, chainF = 0, chainB = 0, totF = 0, totB = 0;
-  int NdS = 0, NdC = 0, stopCode = 0;
-  bool bothPassive = false, candValid = false, forced = false, wIntact = true;
-  int propCur = 0;
-  // diagnostics statistics over used steps (WALNUTS.py:660-692)
-  int sN = 0, sMinIf = 0, sMaxIf = 0, sMinC = 0, sMaxC = 0, sNne = 0, sNz = 0;
-  double sMinL = 0, sMaxL = 0, sHmax = 0, sHmin = 0;
-  bool sHnan = false;
-  // per-pass accumulators
-  double hp = 0.0;
-  bool bad = false;
+  double hh = 0, ha = 0, hp = 0;
+  int expmax = 0;          // max over the pass of the exponent field of the per-thread energy partial
+  unsigned long long totF = 0, totB = 0;
 
-  auto useq = [&]() -> double { return rng_uniform(key, STREAM_SEQ, nseq++); };
-  auto jit = [&](double u) -> double { return __dadd_rn(jlo, __dmul_rn(__dadd_rn(jhi, -jlo), u)); };
-
+  auto useq = [&]() -> double {
+    RngKey key{P.seed_lo, P.seed_hi, C.chain, C.iter};
+    const uint32_t n = C.nseq;
+    C.nseq = n + 1;
+    return rng_uniform(key, STREAM_SEQ, n);
+  };
+  auto jit = [&](double u) -> double {
+    const double lo = C.jlo;
+    return __dadd_rn(lo, __dmul_rn(__dadd_rn(C.jhi, -lo), u));
+  };
   auto save_ck = [&]() {
 #pragma unroll
     for (int e = 0; e < E; ++e) {
@@ -136,13 +134,14 @@ __global__ void __launch_bounds__(NT) walnutspy_kernel(const __grid_constant__ R
   };
   auto start_pass = [&](int cc) {
     steps_left = 1u << cc;
-    hh = ldexp(h, -cc);
+    hh = ldexp(C.h, -cc);
     ha = 0.5 * hh;
-    bad = false;
+    expmax = 0;
   };
   // U-turn criterion, reference WALNUTS.py:95-97; (ql, vl) read from scratch, the other state is the
   // register-resident end (q, xi*v).  Orientation: minus end = more backward state.
   auto uturn_vs = [&](int viq, int viv) -> bool {
+    const double xi = C.xi;
     double x[2] = {0.0, 0.0};
 #pragma unroll
     for (int e2 = 0; e2 < E2; ++e2) {
@@ -157,27 +156,40 @@ __global__ void __launch_bounds__(NT) walnutspy_kernel(const __grid_constant__ R
     Grp::template sum<2>(x, red, parity);
     return (x[0] < 0.0) || (x[1] < 0.0);
   };
+  // one leapfrog micro-step on the registers; reference adaptiveIntegrators.py:79-84 (:50-55 fixed)
+  auto micro_step = [&]() {
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      v[e] = fma(ha, g[e], v[e]);
+      q[e] = fma(hh, v[e], q[e]);
+    }
+    const double lpp = target.lp_grad(q, g, red, parity);
+    double ke0 = 0.0, ke1 = 0.0;   // two partial sums: halves the dependent-FMA chain
+#pragma unroll
+    for (int e = 0; e < E; e += 2) {
+      v[e] = fma(ha, g[e], v[e]);
+      v[e + 1] = fma(ha, g[e + 1], v[e + 1]);
+      ke0 = fma(v[e], v[e], ke0);
+      ke1 = fma(v[e + 1], v[e + 1], ke1);
+    }
+    hp = fma(0.5, ke0 + ke1, -lpp);   // this thread's partial of H_k = -f + 1/2 sum v^2 (:84)
+    // all(isfinite(Hams)) (:92) is tracked on the exponent field with integer ops, off the FP64 pipe
+    expmax = max(expmax, __double2hiint(hp) & 0x7ff00000);
+  };
 
   int st = ST_CHAIN;
   for (;;) {
-    // =============================== hot: one leapfrog micro-step ===============================
+    // =============================== hot: leapfrog micro-steps ==================================
     if (st == ST_RUN) {
-      // reference adaptiveIntegrators.py:79-84 (and :50-55 for fixedLeapFrog)
-#pragma unroll
-      for (int e = 0; e < E; ++e) {
-        v[e] = fma(ha, g[e], v[e]);
-        q[e] = fma(hh, v[e], q[e]);
+      if (steps_left >= 2u) {   // two steps per trip: the tail of one overlaps the head of the next
+        micro_step();
+        micro_step();
+        steps_left -= 2u;
+      } else {
+        micro_step();
+        steps_left = 0u;
       }
-      const double lpp = target.lp_grad(q, g, red, parity);
-      double ke = 0.0;
-#pragma unroll
-      for (int e = 0; e < E; ++e) {
-        v[e] = fma(ha, g[e], v[e]);
-        ke = fma(v[e], v[e], ke);
-      }
-      hp = fma(0.5, ke, -lpp);
-      bad |= !finite_d(hp);
-      if (--steps_left != 0) continue;
+      if (steps_left != 0u) continue;
       st = ST_PASS_END;
     }
     // =============================== cold: per-chain state machine ==============================
@@ -191,30 +203,33 @@ __global__ void __launch_bounds__(NT) walnutspy_kernel(const __grid_constant__ R
             st = ST_EXIT;
             break;
           }
-          chain = (int)cidx;
-          key.chain = P.chain_offset + cidx;
+          C.chain = P.chain_offset + cidx;
 #pragma unroll
           for (int e = 0; e < E; ++e) {
             const int j = coord_of<G>(e, t);
-            q[e] = (j < P.d) ? P.state[(size_t)chain * P.d + j] : 0.0;
+            q[e] = (j < P.d) ? P.state[(size_t)cidx * P.d + j] : 0.0;
           }
-          Hbig = P.Hstep ? P.Hstep[chain] : P.H0;
-          delta = P.delta ? P.delta[chain] : P.delta0;
-          jlo = __dmul_rn(Hbig, __dadd_rn(1.0, -P.jitter));   // WALNUTS.py:298
-          jhi = __dmul_rn(Hbig, __dadd_rn(1.0, P.jitter));
-          it = 0;
-          chainF = chainB = 0;
+          const double Hbig = P.Hstep ? P.Hstep[cidx] : P.H0;
+          C.Hbig = Hbig;
+          C.delta = P.delta ? P.delta[cidx] : P.delta0;
+          C.jlo = __dmul_rn(Hbig, __dadd_rn(1.0, -P.jitter));   // WALNUTS.py:298
+          C.jhi = __dmul_rn(Hbig, __dadd_rn(1.0, P.jitter));
+          C.it = 0;
+          C.chainF = 0;
+          C.chainB = 0;
           st = ST_ITER;
           break;
         }
         case ST_ITER: {  // per-iteration setup, WALNUTS.py:196-276
-          key.iter = P.iter0 + (uint32_t)it;
-          nseq = 0;
-          dirbits = 0;
+          RngKey key{P.seed_lo, P.seed_hi, C.chain, P.iter0 + (uint32_t)C.it};
+          C.iter = key.iter;
+          C.nseq = 0;
+          uint32_t dirbits = 0;
           for (int k = 0; k < P.M; ++k) {
             const double u = rng_uniform(key, STREAM_DIR, (uint32_t)k);   // B = floor(U(0,2)), :216
             dirbits |= (u >= 0.5 ? 1u : 0u) << k;
           }
+          C.dirbits = dirbits;
           double x[1];
           {
             double ke = 0.0;
@@ -232,8 +247,10 @@ __global__ void __launch_bounds__(NT) walnutspy_kernel(const __grid_constant__ R
             x[0] = fma(0.5, ke, -lpp);
           }
           Grp::template sum<1>(x, red, parity);
-          H0 = x[0];                                                      // :256
-          endH0 = endH1 = H0;
+          const double H0 = x[0];                                         // :256
+          C.H0 = H0;
+          C.endH0 = H0;
+          C.endH1 = H0;
 #pragma unroll
           for (int e2 = 0; e2 < E2; ++e2) {   // origin is both ends; it is also the first proposal
             const double2 qq = make_double2(q[2 * e2], q[2 * e2 + 1]);
@@ -242,31 +259,31 @@ __global__ void __launch_bounds__(NT) walnutspy_kernel(const __grid_constant__ R
             *sc(V_PARK_G, e2) = make_double2(g[2 * e2], g[2 * e2 + 1]);
             *sc(V_PROP0, e2) = qq;
           }
-          propCur = 0;
-          lwtSum0 = lwtSum1 = 0.0;
-          timeLen0 = timeLen1 = 0.0;
-          maxInt0 = maxInt1 = 0;
-          WoldSum = 1.0;
-          L_ = 0;
-          indexStat = 0.0;
-          orbitLen = orbitLenSam = 0.0;
-          nF = nB = 0;
-          NdS = NdC = 0;
-          stopCode = 0;
-          bothPassive = false;
-          forced = false;
-          sN = 0;
-          sNne = sNz = 0;
-          sHmax = sHmin = H0;
-          sHnan = false;
-          side = -1;
-          xi = 1.0;
-          level = 0;
+          C.propCur = 0;
+          C.lwtSum0 = 0.0; C.lwtSum1 = 0.0;
+          C.timeLen0 = 0.0; C.timeLen1 = 0.0;
+          C.maxInt0 = 0; C.maxInt1 = 0;
+          C.WoldSum = 1.0;
+          C.L_ = 0;
+          C.indexStat = 0.0;
+          C.orbitLen = 0.0; C.orbitLenSam = 0.0;
+          C.nF = 0; C.nB = 0;
+          C.NdS = 0; C.NdC = 0;
+          C.stopCode = 0;
+          C.bothPassive = 0;
+          C.forced = 0;
+          C.sN = 0; C.sNne = 0; C.sNz = 0;
+          C.sHmax = H0; C.sHmin = H0;
+          C.sHnan = 0;
+          C.side = -1;
+          C.xi = 1.0;
+          C.level = 0;
           st = ST_LEVEL;
           break;
         }
         case ST_LEVEL: {  // start doubling `level`, WALNUTS.py:281-294
-          const int ns = (dirbits >> level) & 1u;   // 0 forward, 1 backward
+          const int level = C.level, side = C.side;
+          const int ns = (C.dirbits >> level) & 1u;   // 0 forward, 1 backward
           const double nxi = ns ? -1.0 : 1.0;
           if (side < 0) {
             // registers hold the origin with forward-time v; switch to integration convention
@@ -274,6 +291,7 @@ __global__ void __launch_bounds__(NT) walnutspy_kernel(const __grid_constant__ R
             for (int e = 0; e < E; ++e) v[e] *= nxi;
           } else if (ns != side) {
             // swap the active end with the parked one (stored in forward-time convention)
+            const double xi = C.xi;
 #pragma unroll
             for (int e2 = 0; e2 < E2; ++e2) {
               const double2 pq = *sc(V_PARK_Q, e2), pv = *sc(V_PARK_V, e2), pg = *sc(V_PARK_G, e2);
@@ -285,99 +303,111 @@ __global__ void __launch_bounds__(NT) walnutspy_kernel(const __grid_constant__ R
               g[2 * e2] = pg.x; g[2 * e2 + 1] = pg.y;
             }
           }
-          side = ns;
-          xi = nxi;
-          nleaf = 0;
-          n_new = 1u << level;
-          WnewSum = 0.0;
-          Lold = L_;
-          indexStatOld = indexStat;
-          candValid = false;
+          C.side = ns;
+          C.xi = nxi;
+          C.nleaf = 0;
+          C.n_new = 1u << level;
+          C.WnewSum = 0.0;
+          C.Lold = C.L_;
+          C.indexStatOld = C.indexStat;
+          C.candValid = 0;
           st = ST_MACRO;
           break;
         }
         case ST_MACRO: {  // start one macro step from the active end
-          ++nleaf;
-          if (level == 0) {
+          const uint32_t nleaf = C.nleaf + 1u;
+          C.nleaf = nleaf;
+          double h;
+          if (C.level == 0) {
             h = jit(useq());              // :298
-            orbitLen += h;                // :300
+            C.orbitLen = C.orbitLen + h;  // :300
           } else if (nleaf & 1u) {
             h = jit(useq());              // :395 (two draws per leaf pair)
-            h2 = jit(useq());
+            C.h2 = jit(useq());
           } else {
-            h = h2;
+            h = C.h2;
           }
-          Ham0 = side ? endH1 : endH0;
-          phase = PH_FWD;
-          c = (P.kind == KIND_FIXED) ? 0 : P.minC;
+          C.h = h;
+          C.Ham0 = C.side ? C.endH1 : C.endH0;
+          C.phase = PH_FWD;
+          const int c0 = (P.kind == KIND_FIXED) ? 0 : P.minC;
+          C.c = c0;
           if (P.kind != KIND_FIXED) save_ck();   // S = start state (integration convention)
-          wIntact = true;
-          start_pass(c);
+          C.wIntact = 1;
+          start_pass(c0);
           st = ST_RUN;
           break;
         }
         case ST_PASS_END: {  // a pass of 2^c micro-steps finished
-          double x[2] = {hp, bad ? 1.0 : 0.0};
+          double x[2] = {hp, (expmax == 0x7ff00000) ? 1.0 : 0.0};
           Grp::template sum<2>(x, red, parity);
           const double Hend = x[0];
           const bool anybad = x[1] != 0.0;
+          const int phase = C.phase;
+          int c = C.c;
           if (phase == PH_FWD) {
-            nF += 1ull << c;
-            const bool ok = !anybad && fabs(Ham0 - Hend) < delta;   // adaptiveIntegrators.py:87-92
+            C.nF = C.nF + (1ull << c);
+            const bool ok = !anybad && fabs(C.Ham0 - Hend) < C.delta;   // adaptiveIntegrators.py:87-92
             if (!(P.kind == KIND_FIXED || ok || c == P.maxC)) {
               ++c;
+              C.c = c;
               load_ck(1.0);
               start_pass(c);
               st = ST_RUN;
               break;
             }
-            If = c;
-            cSim = If;
-            lwtf = 0.0;
+            C.If = c;
+            C.cSim = c;
+            C.lwtf = 0.0;
             if (P.kind == KIND_R2P) {
               if (useq() < P.p0) {              // adaptiveIntegrators.py:392
-                lwtf = P.log_p0;
+                C.lwtf = P.log_p0;
               } else {                          // :400-424 redo at If+1
-                cSim = If + 1;
-                phase = PH_REDO;
+                C.cSim = c + 1;
+                C.phase = PH_REDO;
                 load_ck(1.0);
-                start_pass(cSim);
+                start_pass(c + 1);
                 st = ST_RUN;
                 break;
               }
             }
           } else if (phase == PH_REDO) {
-            nF += 1ull << cSim;
-            lwtf = P.log_1mp0;
+            C.nF = C.nF + (1ull << C.cSim);
+            C.lwtf = P.log_1mp0;
           }
           if (phase != PH_BWD) {
             // forward simulation done: registers hold the out state O
-            Hfwd = Hend;
+            C.Hfwd = Hend;
             if (P.kind == KIND_FIXED) {
-              Ib = 0;
-              lwt = 0.0;
+              C.Ib = 0;
+              C.lwt = 0.0;
               st = ST_LEAF;
               break;
             }
+            const int If = C.If, cSim = C.cSim;
+            int maxTry, Ib;
             if (P.kind == KIND_D || cSim == If) { maxTry = If - 1; Ib = If; }   // :104-111 / :430-433
             else { maxTry = P.maxC; Ib = P.maxC; }                              // :434-437
+            C.maxTry = maxTry;
+            C.Ib = Ib;
             if (maxTry >= P.minC) {
               save_ck();             // O replaces S
-              wIntact = false;
-              phase = PH_BWD;
-              c = P.minC;
+              C.wIntact = 0;
+              C.phase = PH_BWD;
+              C.c = P.minC;
 #pragma unroll
               for (int e = 0; e < E; ++e) v[e] = -v[e];
-              start_pass(c);
+              start_pass(P.minC);
               st = ST_RUN;
               break;
             }
           } else {
-            nB += 1ull << c;
-            const bool ok = !anybad && fabs(Hfwd - Hend) < delta;   // :129-132 / :461-464
-            if (ok) Ib = c;
-            if (!ok && c < maxTry) {
+            C.nB = C.nB + (1ull << c);
+            const bool ok = !anybad && fabs(C.Hfwd - Hend) < C.delta;   // :129-132 / :461-464
+            if (ok) C.Ib = c;
+            if (!ok && c < C.maxTry) {
               ++c;
+              C.c = c;
               load_ck(-1.0);
               start_pass(c);
               st = ST_RUN;
@@ -385,70 +415,80 @@ __global__ void __launch_bounds__(NT) walnutspy_kernel(const __grid_constant__ R
             }
           }
           // macro step complete
-          if (P.kind == KIND_D) {
-            lwt = (If != Ib) ? WN_LOG_ZERO : 0.0;                    // :136
-          } else {
-            double lwtb = WN_LOG_ZERO;                               // :467-471
-            if (cSim == Ib) lwtb = P.log_p0;
-            else if (cSim == Ib + 1) lwtb = P.log_1mp0;
-            lwt = lwtb - lwtf;
+          {
+            const int If = C.If, Ib = C.Ib, cSim = C.cSim;
+            if (P.kind == KIND_D) {
+              C.lwt = (If != Ib) ? WN_LOG_ZERO : 0.0;                  // :136
+            } else {
+              double lwtb = WN_LOG_ZERO;                               // :467-471
+              if (cSim == Ib) lwtb = P.log_p0;
+              else if (cSim == Ib + 1) lwtb = P.log_1mp0;
+              C.lwt = lwtb - C.lwtf;
+            }
           }
-          if (!wIntact) load_ck(1.0);
+          if (!C.wIntact) load_ck(1.0);
           st = ST_LEAF;
           break;
         }
         case ST_LEAF: {  // driver bookkeeping after a macro step, WALNUTS.py:302-368,398-570
-          const int idx = (level == 0) ? (side ? -1 : 1) : (side ? maxInt1 - 1 : maxInt0 + 1);
-          const double tl = (level == 0) ? h : (side ? timeLen1 : timeLen0) + h;
-          if (side) { maxInt1 = idx; timeLen1 = tl; endH1 = Hfwd; }
-          else { maxInt0 = idx; timeLen0 = tl; endH0 = Hfwd; }
+          const int level = C.level, side = C.side;
+          const uint32_t nleaf = C.nleaf;
+          const double h = C.h, Hfwd = C.Hfwd, lwt = C.lwt;
+          const int idx = (level == 0) ? (side ? -1 : 1) : (side ? C.maxInt1 - 1 : C.maxInt0 + 1);
+          const double tl = (level == 0) ? h : (side ? C.timeLen1 : C.timeLen0) + h;
+          if (side) { C.maxInt1 = idx; C.timeLen1 = tl; C.endH1 = Hfwd; }
+          else { C.maxInt0 = idx; C.timeLen0 = tl; C.endH0 = Hfwd; }
           {  // running statistics over used steps
-            const int cs = (P.kind == KIND_FIXED) ? 0 : cSim;
-            if (sN == 0) {
-              sMinIf = sMaxIf = If;
-              sMinC = sMaxC = cs;
-              sMinL = sMaxL = lwt;
+            const int If = C.If, Ib = C.Ib;
+            const int cs = (P.kind == KIND_FIXED) ? 0 : C.cSim;
+            if (C.sN == 0) {
+              C.sMinIf = If; C.sMaxIf = If;
+              C.sMinC = cs; C.sMaxC = cs;
+              C.sMinL = lwt; C.sMaxL = lwt;
             } else {
-              sMinIf = min(sMinIf, If); sMaxIf = max(sMaxIf, If);
-              sMinC = min(sMinC, cs); sMaxC = max(sMaxC, cs);
-              sMinL = fmin(sMinL, lwt); sMaxL = fmax(sMaxL, lwt);
+              C.sMinIf = min(C.sMinIf, If); C.sMaxIf = max(C.sMaxIf, If);
+              C.sMinC = min(C.sMinC, cs); C.sMaxC = max(C.sMaxC, cs);
+              C.sMinL = fmin(C.sMinL, lwt); C.sMaxL = fmax(C.sMaxL, lwt);
             }
-            ++sN;
-            sNne += (If != Ib);
-            sNz += (If == 0);
-            if (Hfwd != Hfwd) sHnan = true;
-            else { sHmax = fmax(sHmax, Hfwd); sHmin = fmin(sHmin, Hfwd); }
+            C.sN = C.sN + 1;
+            C.sNne = C.sNne + (If != Ib);
+            C.sNz = C.sNz + (If == 0);
+            if (Hfwd != Hfwd) C.sHnan = 1;
+            else { C.sHmax = fmax(C.sHmax, Hfwd); C.sHmin = fmin(C.sHmin, Hfwd); }
           }
           if (!finite_d(Hfwd)) {   // forced reject, :316,350,414,457,501,544 (quirks A14 ii, iii)
-            forced = true;
-            if (level == 0 || (nleaf & 1u)) stopCode = 999;
+            C.forced = 1;
+            if (level == 0 || (nleaf & 1u)) C.stopCode = 999;
             st = ST_ITER_END;
             break;
           }
-          double ls = side ? lwtSum1 : lwtSum0;
+          double ls = side ? C.lwtSum1 : C.lwtSum0;
           if (level == 0) ls = lwt;                                                  // :321,354
           else if (!(side == 1 && !(nleaf & 1u))) ls += lwt;                         // :420,507,550; quirk A14(i)
-          if (side) lwtSum1 = ls; else lwtSum0 = ls;
-          const double Wnew = exp(-Hfwd + H0 + ls);                                  // :322,...
+          if (side) C.lwtSum1 = ls; else C.lwtSum0 = ls;
+          const double Wnew = exp(-Hfwd + C.H0 + ls);                                // :322,...
           bool pick;
           if (level == 0) {
-            WnewSum = Wnew;
+            C.WnewSum = Wnew;
             pick = true;                                                            // :326,359
           } else {
-            WnewSum += Wnew;
+            const double ws = C.WnewSum + Wnew;
+            C.WnewSum = ws;
             pick = false;
-            if (WnewSum > WN_WT_SUM_THRESH) pick = useq() < Wnew / WnewSum;          // :426,464,512,554
-            orbitLen += h;                                                          // :432,...
+            if (ws > WN_WT_SUM_THRESH) pick = useq() < Wnew / ws;                    // :426,464,512,554
+            C.orbitLen = C.orbitLen + h;                                            // :432,...
           }
           if (pick) {
+            const int pv = V_PROP0 + (C.propCur ^ 1);
 #pragma unroll
-            for (int e2 = 0; e2 < E2; ++e2) *sc(V_PROP0 + (propCur ^ 1), e2) = make_double2(q[2 * e2], q[2 * e2 + 1]);
-            candValid = true;
-            L_ = idx;
-            indexStat = side ? -tl : tl;
+            for (int e2 = 0; e2 < E2; ++e2) *sc(pv, e2) = make_double2(q[2 * e2], q[2 * e2 + 1]);
+            C.candValid = 1;
+            C.L_ = idx;
+            C.indexStat = side ? -tl : tl;
           }
           bool sub = false;
           if (level > 0) {
+            const double xi = C.xi;
             if (nleaf & 1u) {
               // left end of the pending dyadic levels 1..ctz(nleaf-1) (all when nleaf == 1)
               const int lvl = (nleaf == 1u) ? level : (__ffs(nleaf - 1u) - 1);
@@ -470,51 +510,56 @@ __global__ void __launch_bounds__(NT) walnutspy_kernel(const __grid_constant__ R
             }
           }
           if (sub) {                         // :597-605
-            indexStat = indexStat / (timeLen0 + timeLen1);
-            candValid = false;
-            L_ = Lold;
-            indexStat = indexStatOld;
-            NdS = level;
-            NdC = level + 1;
-            stopCode = 5;
+            C.candValid = 0;
+            C.L_ = C.Lold;
+            C.indexStat = C.indexStatOld;
+            C.NdS = level;
+            C.NdC = level + 1;
+            C.stopCode = 5;
             st = ST_ITER_END;
           } else {
-            st = (nleaf == n_new) ? ST_LEVEL_END : ST_MACRO;
+            st = (nleaf == C.n_new) ? ST_LEVEL_END : ST_MACRO;
           }
           break;
         }
         case ST_LEVEL_END: {  // WALNUTS.py:595-648
-          indexStat = indexStat / (timeLen0 + timeLen1);                         // :595
-          if (!(useq() < WnewSum / WoldSum)) {                                       // :613
-            L_ = Lold;
-            indexStat = indexStatOld;
-          } else if (candValid) {
-            propCur ^= 1;
+          const int level = C.level;
+          const double ws = C.WnewSum, wo = C.WoldSum;
+          C.indexStat = C.indexStat / (C.timeLen0 + C.timeLen1);                     // :595
+          if (!(useq() < ws / wo)) {                                                 // :613
+            C.L_ = C.Lold;
+            C.indexStat = C.indexStatOld;
+          } else if (C.candValid) {
+            C.propCur = C.propCur ^ 1;
           }
-          candValid = false;
+          C.candValid = 0;
           const bool joined = uturn_vs(V_PARK_Q, V_PARK_V);                          // :622
-          bothPassive = (lwtSum1 < WN_LOG_ZERO + 1.0) && (lwtSum0 < WN_LOG_ZERO + 1.0);   // :624
-          NdS = NdC = level + 1;
-          orbitLenSam = orbitLen;
+          const bool bothPassive = (C.lwtSum1 < WN_LOG_ZERO + 1.0) && (C.lwtSum0 < WN_LOG_ZERO + 1.0);   // :624
+          C.bothPassive = bothPassive;
+          C.NdS = level + 1;
+          C.NdC = level + 1;
+          C.orbitLenSam = C.orbitLen;
           if (joined || bothPassive) {
-            stopCode = joined ? 4 : -4;
+            C.stopCode = joined ? 4 : -4;
             st = ST_ITER_END;
             break;
           }
-          WoldSum += WnewSum;                                                        // :641
-          ++level;
-          st = (level == P.M) ? ST_ITER_END : ST_LEVEL;
+          C.WoldSum = wo + ws;                                                       // :641
+          C.level = level + 1;
+          st = (level + 1 == P.M) ? ST_ITER_END : ST_LEVEL;
           break;
         }
         case ST_ITER_END: {  // qc = qProp; outputs, WALNUTS.py:653-695
-          const int pv = V_PROP0 + ((forced && candValid) ? (propCur ^ 1) : propCur);
+          const int pv = V_PROP0 + ((C.forced && C.candValid) ? (C.propCur ^ 1) : C.propCur);
 #pragma unroll
           for (int e2 = 0; e2 < E2; ++e2) {
             const double2 qq = *sc(pv, e2);
             q[2 * e2] = qq.x;
             q[2 * e2 + 1] = qq.y;
           }
-          const size_t row = (size_t)it * P.n_chains + chain;
+          const uint32_t cidx = C.chain - P.chain_offset;
+          const int it = C.it;
+          const size_t row = (size_t)it * P.n_chains + cidx;
           if (P.draws) {
 #pragma unroll
             for (int e = 0; e < E; ++e) {
@@ -522,37 +567,39 @@ __global__ void __launch_bounds__(NT) walnutspy_kernel(const __grid_constant__ R
               if (j < P.dg) P.draws[row * P.dg + j] = q[e];
             }
           }
+          const unsigned long long nF = C.nF, nB = C.nB;
           if (P.diag && t == 0) {
             double* dg = P.diag + row * 24;
-            const double n = (double)sN;
-            dg[0] = L_; dg[1] = NdS; dg[2] = orbitLen; dg[3] = orbitLenSam;
-            dg[4] = maxInt0; dg[5] = maxInt1; dg[6] = (double)nF; dg[7] = (double)nB;
-            dg[8] = sMinIf; dg[9] = sMaxIf; dg[10] = sMinL; dg[11] = sMaxL;
-            dg[12] = bothPassive ? 1.0 : 0.0;
-            dg[13] = ((lwtSum1 < WN_LOG_ZERO + 1.0) || (lwtSum0 < WN_LOG_ZERO + 1.0)) ? 1.0 : 0.0;
-            dg[14] = (double)sNne / n; dg[15] = Hbig; dg[16] = (double)sNz / n;
-            dg[17] = sHnan ? __longlong_as_double(0x7ff8000000000000ll) : sHmax - sHmin;
-            dg[18] = delta; dg[19] = stopCode; dg[20] = NdC; dg[21] = sMinC; dg[22] = sMaxC;
-            dg[23] = indexStat;
+            const double n = (double)C.sN;
+            dg[0] = C.L_; dg[1] = C.NdS; dg[2] = C.orbitLen; dg[3] = C.orbitLenSam;
+            dg[4] = C.maxInt0; dg[5] = C.maxInt1; dg[6] = (double)nF; dg[7] = (double)nB;
+            dg[8] = C.sMinIf; dg[9] = C.sMaxIf; dg[10] = C.sMinL; dg[11] = C.sMaxL;
+            dg[12] = C.bothPassive ? 1.0 : 0.0;
+            dg[13] = ((C.lwtSum1 < WN_LOG_ZERO + 1.0) || (C.lwtSum0 < WN_LOG_ZERO + 1.0)) ? 1.0 : 0.0;
+            dg[14] = (double)C.sNne / n; dg[15] = C.Hbig; dg[16] = (double)C.sNz / n;
+            dg[17] = C.sHnan ? __longlong_as_double(0x7ff8000000000000ll) : C.sHmax - C.sHmin;
+            dg[18] = C.delta; dg[19] = C.stopCode; dg[20] = C.NdC; dg[21] = C.sMinC; dg[22] = C.sMaxC;
+            dg[23] = C.indexStat;
           }
-          chainF += nF;
-          chainB += nB;
-          ++it;
-          if (it < P.n_iter) {
+          const unsigned long long cf = C.chainF + nF, cbk = C.chainB + nB;
+          C.chainF = cf;
+          C.chainB = cbk;
+          C.it = it + 1;
+          if (it + 1 < P.n_iter) {
             st = ST_ITER;
             break;
           }
 #pragma unroll
           for (int e = 0; e < E; ++e) {
             const int j = coord_of<G>(e, t);
-            if (j < P.d) P.state[(size_t)chain * P.d + j] = q[e];
+            if (j < P.d) P.state[(size_t)cidx * P.d + j] = q[e];
           }
           if (t == 0) {
-            if (P.nevalF) P.nevalF[chain] = chainF;
-            if (P.nevalB) P.nevalB[chain] = chainB;
+            if (P.nevalF) P.nevalF[cidx] = cf;
+            if (P.nevalB) P.nevalB[cidx] = cbk;
           }
-          totF += chainF;
-          totB += chainB;
+          totF += cf;
+          totB += cbk;
           st = ST_CHAIN;
           break;
         }
