@@ -24,6 +24,8 @@ def oracle_target(name, d, data=None):
         return otargets.funnel10
     if name == "corr_gauss":
         return otargets.corr_gauss
+    if name == "stock_watson":
+        return otargets.make_stock_watson(data["y"])
     raise KeyError(name)
 
 

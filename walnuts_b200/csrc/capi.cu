@@ -68,7 +68,7 @@ static LaunchPlan plan_wpy() {
   LaunchPlan p;
   p.fn = (const void*)walnutspy_kernel<T, G, E2, NT, MINB>;
   p.G = G; p.E2 = E2; p.NT = NT;
-  p.smem = (size_t)(3 * 2 * E2 * NT + 2 * ((G + 31) / 32) * 4) * sizeof(double);
+  p.smem = (size_t)(3 * 2 * E2 * NT + 2 * ((G + 31) / 32) * 8) * sizeof(double);
   p.package = false;
   return p;
 }
@@ -77,7 +77,7 @@ static LaunchPlan plan_pkg() {
   LaunchPlan p;
   p.fn = (const void*)package_kernel<T, G, E2, NT>;
   p.G = G; p.E2 = E2; p.NT = NT;
-  p.smem = (size_t)(3 * 2 * E2 * NT + 2 * ((G + 31) / 32) * 4) * sizeof(double);
+  p.smem = (size_t)(3 * 2 * E2 * NT + 2 * ((G + 31) / 32) * 8) * sizeof(double);
   p.package = true;
   return p;
 }
@@ -131,6 +131,14 @@ static bool pick_plan(const wn_config& c, LaunchPlan& p) {
     }
     case WN_TARGET_FUNNEL: return pick_warp<FunnelT>(pkg, c.d, p);
     case WN_TARGET_FUNNEL_PKG: return pick_warp<FunnelPkgT>(pkg, c.d, p);
+    case WN_TARGET_STOCK_WATSON: {
+      // d = 3T; thread t owns B consecutive time steps: T <= G*B
+      if (c.d % 3 != 0) return false;
+      const int T = c.d / 3;
+      if (T <= 64 * 4) { p = pkg ? plan_pkg<StockWatsonT, 64, 7, 64>() : plan_wpy<StockWatsonT, 64, 7, 64>(); return true; }
+      if (T <= 128 * 4) { p = pkg ? plan_pkg<StockWatsonT, 128, 7, 128>() : plan_wpy<StockWatsonT, 128, 7, 128>(); return true; }
+      return false;
+    }
     case WN_TARGET_CORR_GAUSS:
       if (c.d != 2) return false;
       p = pkg ? plan_pkg<CorrGaussT, 1, 1, 128>() : plan_wpy<CorrGaussT, 1, 1, 128>();
@@ -310,6 +318,8 @@ int wn_run_async(wn_handle* h, int64_t n_iter, double* d_draws, double* d_diag, 
   if (!h->have_state) return fail(h, WN_ESTATE, "wn_run before wn_set_state");
   const wn_config& c = h->cfg;
   if (c.target == WN_TARGET_DIAG_GAUSS && !h->d_p0) return fail(h, WN_ESTATE, "diag_gauss needs data key inv_var");
+  if (c.target == WN_TARGET_STOCK_WATSON && (!h->d_p0 || h->n_p0 * 3 != c.d))
+    return fail(h, WN_ESTATE, "stock_watson needs data key y with T = d/3 entries");
   if (c.mode == WN_MODE_PACKAGE && !h->d_inv_mass) return fail(h, WN_ESTATE, "package mode needs data key inv_mass");
   LaunchPlan p;
   if (!pick_plan(c, p)) return fail(h, WN_EUNSUPPORTED, "no CUDA kernel for this target/dimension");

@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(NT, MINB) package_kernel(const __grid_constant
   double q[E], v[E], g[E], im[E], sim[E];
 #pragma unroll
   for (int e = 0; e < E; ++e) {
-    const int j = coord_of<G>(e, t);
+    const int j = target.coord(e, t);
     im[e] = (j < P.d) ? P.inv_mass[j] : 0.0;
     sim[e] = 0.0;
   }
@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(NT, MINB) package_kernel(const __grid_constant
           C.chain = P.chain_offset + cidx;
 #pragma unroll
           for (int e = 0; e < E; ++e) {
-            const int j = coord_of<G>(e, t);
+            const int j = target.coord(e, t);
             q[e] = (j < P.d) ? P.state[(size_t)cidx * P.d + j] : 0.0;
           }
           C.it = 0;
@@ -241,14 +241,12 @@ __global__ void __launch_bounds__(NT, MINB) package_kernel(const __grid_constant
           {
             double ke = 0.0;
 #pragma unroll
-            for (int e2 = 0; e2 < E2; ++e2) {   // rho = inv_mass**-0.5 * N(0, I), :322-325
-              double z0, z1;
-              const int p = e2 * G + t;
-              rng_normal_pair(key, STREAM_MOM, (uint32_t)p, z0, z1);
-              v[2 * e2] = (2 * p < P.d) ? __dmul_rn(pow(im[2 * e2], -0.5), z0) : 0.0;
-              v[2 * e2 + 1] = (2 * p + 1 < P.d) ? __dmul_rn(pow(im[2 * e2 + 1], -0.5), z1) : 0.0;
-              ke = fma(im[2 * e2] * v[2 * e2], v[2 * e2], ke);
-              ke = fma(im[2 * e2 + 1] * v[2 * e2 + 1], v[2 * e2 + 1], ke);
+            for (int e = 0; e < E; ++e) {   // rho = inv_mass**-0.5 * N(0, I), :322-325
+              const int j = target.coord(e, t);
+              double z0 = 0.0, z1 = 0.0;
+              if (j < P.d) rng_normal_pair(key, STREAM_MOM, (uint32_t)(j >> 1), z0, z1);
+              v[e] = (j < P.d) ? __dmul_rn(pow(im[e], -0.5), (j & 1) ? z1 : z0) : 0.0;
+              ke = fma(im[e] * v[e], v[e], ke);
             }
             x[0] = target.lp_grad(q, g, red, parity);
             x[1] = ke;
@@ -481,7 +479,7 @@ __global__ void __launch_bounds__(NT, MINB) package_kernel(const __grid_constant
           if (P.draws) {
 #pragma unroll
             for (int e = 0; e < E; ++e) {
-              const int j = coord_of<G>(e, t);
+              const int j = target.coord(e, t);
               if (j < P.dg) P.draws[row * P.dg + j] = q[e];
             }
           }
@@ -494,7 +492,7 @@ __global__ void __launch_bounds__(NT, MINB) package_kernel(const __grid_constant
           }
 #pragma unroll
           for (int e = 0; e < E; ++e) {
-            const int j = coord_of<G>(e, t);
+            const int j = target.coord(e, t);
             if (j < P.d) P.state[(size_t)cidx * P.d + j] = q[e];
           }
           if (t == 0 && P.neval) P.neval[cidx] = ce;

@@ -29,6 +29,8 @@ __device__ __forceinline__ int coord_of(int e, int t) {
 template <int G, int E2, bool UNIT>
 struct DiagGaussT {
   static constexpr int E = 2 * E2;
+  static constexpr bool PAIR_LAYOUT = true;
+  __device__ __forceinline__ int coord(int e, int t) const { return coord_of<G>(e, t); }
   double s[UNIT ? 1 : E];
   __device__ __forceinline__ void init(const TargetParams& tp, int d, int t) {
     if constexpr (!UNIT) {
@@ -57,6 +59,8 @@ struct DiagGaussT {
 template <int G, int E2>
 struct FunnelT {
   static constexpr int E = 2 * E2;
+  static constexpr bool PAIR_LAYOUT = true;
+  __device__ __forceinline__ int coord(int e, int t) const { return coord_of<G>(e, t); }
   static_assert(G <= 32, "funnel target needs the chain inside one warp");
   int d_;
   double nn;
@@ -96,6 +100,8 @@ struct FunnelT {
 template <int G, int E2>
 struct FunnelPkgT {
   static constexpr int E = 2 * E2;
+  static constexpr bool PAIR_LAYOUT = true;
+  __device__ __forceinline__ int coord(int e, int t) const { return coord_of<G>(e, t); }
   static_assert(G <= 32, "funnel target needs the chain inside one warp");
   int d_;
   __device__ __forceinline__ void init(const TargetParams&, int d, int) { d_ = d; }
@@ -128,6 +134,8 @@ struct FunnelPkgT {
 template <int G, int E2>
 struct CorrGaussT {
   static constexpr int E = 2 * E2;
+  static constexpr bool PAIR_LAYOUT = true;
+  __device__ __forceinline__ int coord(int e, int t) const { return coord_of<G>(e, t); }
   static_assert(G == 1 && E2 == 1, "corr_gauss is 2-d");
   __device__ __forceinline__ void init(const TargetParams&, int, int) {}
   __device__ __forceinline__ double lp_grad(const double (&q)[E], double (&g)[E], double*, int&) const {
@@ -136,6 +144,190 @@ struct CorrGaussT {
     g[0] = -(q[0] - rho * q[1]) / tmp;
     g[1] = -(q[1] - rho * q[0]) / tmp;
     return -0.5 * q[0] * q[0] - (0.5 / tmp) * (r * r);
+  }
+};
+
+}  // namespace wn
+
+namespace wn {
+
+// ---- T5: Stock-Watson stochastic volatility ------------------------------------------------------
+// Unconstrained parameterisation of reference WALNUTSpy_examples/StockWatson/sw_innov.stan:7-52
+// (bridgestan, propto = True); formulas: SURVEY.md appendix B, restated in oracle/targets.py
+// (make_stock_watson).  theta = [tS, z1, zinn[T-2], x1, xinn[T-1], tau1, tauinn[T-1]], d = 3T.
+//
+// Layout: time-aligned.  Thread t owns the B consecutive time indices k = t*B .. t*B+B-1 of the three
+// series Z = [z1, zinn...], X = [x1, xinn...], U = [tau1, tauinn...] (elements 0..3B-1) and thread 0
+// additionally owns tS (element 3B).  One evaluation = 2 forward and 2 reverse block scans over the
+// group (warp shuffles + one shared-memory exchange per scan when the chain spans several warps).
+template <int G, int E2>
+struct StockWatsonT {
+  static constexpr int E = 2 * E2;
+  static constexpr int B = (E - 2) / 3;
+  static constexpr bool PAIR_LAYOUT = false;
+  static constexpr int WARPS = (G + 31) / 32;
+  static_assert(3 * B + 2 == E, "E must be 3B + 2");
+  static_assert(G % 32 == 0, "Stock-Watson target needs whole warps per chain");
+  int T;
+  double y[B];
+
+  __device__ __forceinline__ void init(const TargetParams& tp, int, int t) {
+    T = tp.n0;
+#pragma unroll
+    for (int i = 0; i < B; ++i) {
+      const int k = t * B + i;
+      y[i] = (k < T) ? tp.p0[k] : 0.0;
+    }
+  }
+  __device__ __forceinline__ int coord(int e, int t) const {
+    const int BIG = 1 << 30;
+    if (e < B) { const int k = t * B + e; return (k <= T - 2) ? k + 1 : BIG; }                 // z1, zinn
+    if (e < 2 * B) { const int k = t * B + (e - B); return (k <= T - 1) ? T + k : BIG; }       // x1, xinn
+    if (e < 3 * B) { const int k = t * B + (e - 2 * B); return (k <= T - 1) ? 2 * T + k : BIG; } // tau1, tauinn
+    if (e == 3 * B) return (t == 0) ? 0 : BIG;                                                 // tS
+    return BIG;
+  }
+
+  // inclusive scan over the threads of the group of NV channels; FWD: prefix, else suffix.
+  // On return x = inclusive value, ex = exclusive value (sum over strictly preceding / following threads).
+  template <int NV, bool FWD>
+  __device__ __forceinline__ static void scan(double (&x)[NV], double (&ex)[NV], double* red, int& parity) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const double yv = FWD ? __shfl_up_sync(0xffffffffu, x[k], off) : __shfl_down_sync(0xffffffffu, x[k], off);
+        const bool take = FWD ? (lane >= off) : (lane + off < 32);
+        x[k] += take ? yv : 0.0;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const double yv = FWD ? __shfl_up_sync(0xffffffffu, x[k], 1) : __shfl_down_sync(0xffffffffu, x[k], 1);
+      ex[k] = (FWD ? (lane >= 1) : (lane < 31)) ? yv : 0.0;
+    }
+    if constexpr (G > 32) {
+      const int w = (threadIdx.x % G) >> 5;
+      double* buf = red + parity * (WARPS * 8);
+      if (lane == (FWD ? 31 : 0)) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) buf[w * 8 + k] = x[k];
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        double off = 0.0;
+        if (FWD) { for (int ww = 0; ww < w; ++ww) off += buf[ww * 8 + k]; }
+        else { for (int ww = WARPS - 1; ww > w; --ww) off += buf[ww * 8 + k]; }
+        x[k] += off;
+        ex[k] += off;
+      }
+      parity ^= 1;
+    }
+  }
+
+  __device__ __forceinline__ double lp_grad(const double (&q)[E], double (&g)[E], double* red, int& parity) const {
+    const int t = threadIdx.x % G;
+    const int k0 = t * B;
+    // ---- phase 1: prefix sums of the innovations; index-0 entries and tS travel as "base" channels ----
+    double locZ[B], locX[B];
+    double ch[5] = {0.0, 0.0, 0.0, 0.0, 0.0}, ex1[5];
+#pragma unroll
+    for (int i = 0; i < B; ++i) {
+      const int k = k0 + i;
+      const double zi = (k >= 1 && k <= T - 2) ? q[i] : 0.0;
+      const double xi = (k >= 1 && k <= T - 1) ? q[B + i] : 0.0;
+      ch[0] += zi;
+      ch[1] += xi;
+      locZ[i] = ch[0];      // local inclusive prefix
+      locX[i] = ch[1];
+    }
+    if (t == 0) { ch[2] = q[0]; ch[3] = q[B]; ch[4] = q[3 * B]; }
+    scan<5, true>(ch, ex1, red, parity);
+    const double Z0 = ch[2], X0 = ch[3], tS = ch[4];
+    const double sigma = exp(-0.5 * tS), etS = exp(tS);
+    double z[B], ez[B], xx[B], w[B], c[B];
+    double ch2[2] = {0.0, 0.0}, ex2[2];
+    const double ez_prev = exp(0.5 * fma(sigma, ex1[0], Z0));   // exp(z_{k0-1}/2)
+    double locC[B];
+#pragma unroll
+    for (int i = 0; i < B; ++i) {
+      const int k = k0 + i;
+      z[i] = fma(sigma, ex1[0] + locZ[i], Z0);
+      xx[i] = fma(sigma, ex1[1] + locX[i], X0);
+      ez[i] = exp(0.5 * z[i]);
+      w[i] = exp(-xx[i]);
+      const double ezm = (i == 0) ? ez_prev : ez[(i > 0) ? i - 1 : 0];
+      c[i] = (k >= 1 && k <= T - 1) ? ezm * q[2 * B + i] : 0.0;   // exp(z_{k-1}/2) * tauinn_{k-1}
+      ch2[0] += c[i];
+      locC[i] = ch2[0];
+    }
+    if (t == 0) ch2[1] = q[2 * B];
+    // ---- phase 2: tau ----
+    scan<2, true>(ch2, ex2, red, parity);
+    const double U0 = ch2[1];
+    double lp = 0.0;
+    double r[B], a[B];
+    double ch3[2] = {0.0, 0.0}, ex3[2];
+#pragma unroll
+    for (int i = 0; i < B; ++i) {
+      const int k = k0 + i;
+      const bool obs = (k <= T - 1);
+      const double tau = U0 + (ex2[0] + locC[i]);
+      const double e = y[i] - tau;
+      const double eew = e * e * w[i];
+      r[i] = obs ? e * w[i] : 0.0;
+      a[i] = obs ? (-0.5 + 0.5 * eew) : 0.0;
+      if (obs) lp += -0.5 * xx[i] - 0.5 * eew;
+      if (k >= 1 && k <= T - 2) lp -= 0.5 * q[i] * q[i];
+      if (k >= 1 && k <= T - 1) lp -= 0.5 * (q[B + i] * q[B + i] + q[2 * B + i] * q[2 * B + i]);
+    }
+    // local suffix sums
+    double sufR[B], sufA[B];
+#pragma unroll
+    for (int i = B - 1; i >= 0; --i) {
+      ch3[0] += r[i];
+      ch3[1] += a[i];
+      sufR[i] = ch3[0];
+      sufA[i] = ch3[1];
+    }
+    // ---- phase 3: R, A suffix sums ----
+    scan<2, false>(ch3, ex3, red, parity);
+    double bb[B], Rk[B], Ak[B];
+    double ch4[2] = {0.0, 0.0}, ex4[2];
+#pragma unroll
+    for (int i = 0; i < B; ++i) {
+      Rk[i] = ex3[0] + sufR[i];
+      Ak[i] = ex3[1] + sufA[i];
+      bb[i] = 0.5 * c[i] * Rk[i];            // b_{k-1} of appendix B (c is already masked)
+    }
+    double sufB[B];
+#pragma unroll
+    for (int i = B - 1; i >= 0; --i) {
+      const int k = k0 + i;
+      sufB[i] = ch4[0];                       // exclusive local suffix
+      ch4[0] += bb[i];
+      // d/dtS partial: sum_k zinn_k Bz_{k+1} + sum_k xinn_k A_{k+1}, with the first sum re-ordered as
+      // sum_j b_j * (prefix of zinn before j)
+      const double pzex = (ex1[0] + locZ[i]) - ((k >= 1 && k <= T - 2) ? q[i] : 0.0);
+      ch4[1] += bb[i] * pzex + ((k >= 1 && k <= T - 1) ? q[B + i] * Ak[i] : 0.0);
+    }
+    // ---- phase 4: Bz suffix sums and the tS total ----
+    scan<2, false>(ch4, ex4, red, parity);
+#pragma unroll
+    for (int i = 0; i < B; ++i) {
+      const int k = k0 + i;
+      const double Sx = ex4[0] + sufB[i];     // sum_{j > k} bb_j = Bz of appendix B at the next index
+      const double ezm = (i == 0) ? ez_prev : ez[(i > 0) ? i - 1 : 0];
+      g[i] = (k == 0) ? Sx : ((k <= T - 2) ? fma(sigma, Sx, -q[i]) : 0.0);
+      g[B + i] = (k == 0) ? Ak[i] : ((k <= T - 1) ? fma(sigma, Ak[i], -q[B + i]) : 0.0);
+      g[2 * B + i] = (k == 0) ? Rk[i] : ((k <= T - 1) ? fma(ezm, Rk[i], -q[2 * B + i]) : 0.0);
+    }
+    g[3 * B] = (t == 0) ? (5.0 - 0.5 * etS - 0.5 * sigma * ch4[1]) : 0.0;
+    g[3 * B + 1] = 0.0;
+    if (t == 0) lp += 5.0 * tS - 0.5 * etS;
+    return lp;
   }
 };
 

@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
           C.chain = P.chain_offset + cidx;
 #pragma unroll
           for (int e = 0; e < E; ++e) {
-            const int j = coord_of<G>(e, t);
+            const int j = target.coord(e, t);
             q[e] = (j < P.d) ? P.state[(size_t)cidx * P.d + j] : 0.0;
           }
           const double Hbig = P.Hstep ? P.Hstep[cidx] : P.H0;
@@ -233,16 +233,26 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
           double x[1];
           {
             double ke = 0.0;
+            if constexpr (Target::PAIR_LAYOUT) {
 #pragma unroll
-            for (int e2 = 0; e2 < E2; ++e2) {   // v ~ N(0, I), :236
-              double z0, z1;
-              const int p = e2 * G + t;
-              rng_normal_pair(key, STREAM_MOM, (uint32_t)p, z0, z1);
-              v[2 * e2] = (2 * p < P.d) ? z0 : 0.0;
-              v[2 * e2 + 1] = (2 * p + 1 < P.d) ? z1 : 0.0;
-              ke = fma(v[2 * e2], v[2 * e2], ke);
-              ke = fma(v[2 * e2 + 1], v[2 * e2 + 1], ke);
+              for (int e2 = 0; e2 < E2; ++e2) {   // v ~ N(0, I), :236
+                double z0, z1;
+                const int p = e2 * G + t;
+                rng_normal_pair(key, STREAM_MOM, (uint32_t)p, z0, z1);
+                v[2 * e2] = (2 * p < P.d) ? z0 : 0.0;
+                v[2 * e2 + 1] = (2 * p + 1 < P.d) ? z1 : 0.0;
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < E; ++e) {       // same normals, addressed by coordinate
+                const int j = target.coord(e, t);
+                double z0 = 0.0, z1 = 0.0;
+                if (j < P.d) rng_normal_pair(key, STREAM_MOM, (uint32_t)(j >> 1), z0, z1);
+                v[e] = (j < P.d) ? ((j & 1) ? z1 : z0) : 0.0;
+              }
             }
+#pragma unroll
+            for (int e = 0; e < E; ++e) ke = fma(v[e], v[e], ke);
             const double lpp = target.lp_grad(q, g, red, parity);        // :249
             x[0] = fma(0.5, ke, -lpp);
           }
@@ -563,7 +573,7 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
           if (P.draws) {
 #pragma unroll
             for (int e = 0; e < E; ++e) {
-              const int j = coord_of<G>(e, t);
+              const int j = target.coord(e, t);
               if (j < P.dg) P.draws[row * P.dg + j] = q[e];
             }
           }
@@ -591,7 +601,7 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
           }
 #pragma unroll
           for (int e = 0; e < E; ++e) {
-            const int j = coord_of<G>(e, t);
+            const int j = target.coord(e, t);
             if (j < P.d) P.state[(size_t)cidx * P.d + j] = q[e];
           }
           if (t == 0) {

@@ -42,6 +42,14 @@ def ill_conditioned_gauss(d=1000, lo=-2.0, hi=2.0):
     return diag_gauss(np.logspace(lo, hi, d))
 
 
+def stock_watson(y):
+    """Stock-Watson stochastic-volatility model of the reference's example
+    (WALNUTSpy_examples/StockWatson/sw_innov.stan:2-52, bridgestan default propto=True) on the
+    unconstrained scale; `y` is the observed series (T values), d = 3T."""
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    return Target("stock_watson", data={"y": y}, d=3 * y.size, ref="sw_innov.stan:2-52")
+
+
 def resolve(target, d):
     """Target handle (or registry name) -> (name, data) after checking the dimension."""
     if isinstance(target, str):
