@@ -24,6 +24,8 @@ def oracle_target(name, d, data=None):
         return otargets.funnel10
     if name == "corr_gauss":
         return otargets.corr_gauss
+    if name == "logreg":
+        return otargets.make_logreg(data["X"], data["y"], float(np.asarray(data.get("tau", 1.0)).ravel()[0]))
     if name == "stock_watson":
         return otargets.make_stock_watson(data["y"])
     raise KeyError(name)

@@ -238,3 +238,16 @@ def test_stock_watson_small_T(cuda_lib):
     # energies are sensitive to rounding in the unstable region: looser tolerance for that diagnostic only
     check("stock_watson", sw_q0(4, 37), "R2P", H0=0.1, delta=0.3, M=6, n_iter=6, minC=1, data={"y": y},
           float_rtol=1e-6)
+
+
+@pytest.mark.parametrize("integrator,N,P", [("fixed", 500, 7), ("R2P", 500, 7), ("D", 1000, 100), ("R2P", 1333, 100)])
+def test_logreg(cuda_lib, integrator, N, P):
+    """BASELINE config 4 target (P = 100 features) on small synthetic row counts, incl. a ragged N."""
+    from oracle import targets as ot
+    X, y, _ = ot.synth_logreg_data(N=N, P=P, seed=0)
+    data = {"X": X, "y": y, "tau": np.array([1.0])}
+    q0 = 0.3 * np.random.default_rng(4).standard_normal((9, P))
+    H0 = 0.25 if P == 7 else 0.12
+    if integrator == "fixed":
+        H0 *= 0.5
+    check("logreg", q0, integrator, H0=H0, delta=0.3, M=6, n_iter=8, data=data, chains=[0, 4, 8], float_rtol=1e-8)

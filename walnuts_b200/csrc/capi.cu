@@ -24,6 +24,7 @@ struct wn_handle {
   unsigned long long* d_totals = nullptr;
   double* d_p0 = nullptr;  // inv_var | X | y(T)
   double* d_p1 = nullptr;  // y(N)
+  double* d_p2 = nullptr;  // X^T (logreg)
   double* d_inv_mass = nullptr;
   double* d_H = nullptr;
   double* d_delta = nullptr;
@@ -68,7 +69,7 @@ static LaunchPlan plan_wpy() {
   LaunchPlan p;
   p.fn = (const void*)walnutspy_kernel<T, G, E2, NT, MINB>;
   p.G = G; p.E2 = E2; p.NT = NT;
-  p.smem = (size_t)(3 * 2 * E2 * NT + 2 * ((G + 31) / 32) * 8) * sizeof(double);
+  p.smem = (size_t)(3 * 2 * E2 * NT + 2 * ((G + 31) / 32) * 8 + T<G, E2>::smem_doubles(NT)) * sizeof(double);
   p.package = false;
   return p;
 }
@@ -77,7 +78,7 @@ static LaunchPlan plan_pkg() {
   LaunchPlan p;
   p.fn = (const void*)package_kernel<T, G, E2, NT>;
   p.G = G; p.E2 = E2; p.NT = NT;
-  p.smem = (size_t)(3 * 2 * E2 * NT + 2 * ((G + 31) / 32) * 8) * sizeof(double);
+  p.smem = (size_t)(3 * 2 * E2 * NT + 2 * ((G + 31) / 32) * 8 + T<G, E2>::smem_doubles(NT)) * sizeof(double);
   p.package = true;
   return p;
 }
@@ -131,6 +132,10 @@ static bool pick_plan(const wn_config& c, LaunchPlan& p) {
     }
     case WN_TARGET_FUNNEL: return pick_warp<FunnelT>(pkg, c.d, p);
     case WN_TARGET_FUNNEL_PKG: return pick_warp<FunnelPkgT>(pkg, c.d, p);
+    case WN_TARGET_LOGREG:
+      if (c.d > 128) return false;
+      p = pkg ? plan_pkg<LogRegT, 32, 2, 256>() : plan_wpy<LogRegT, 32, 2, 256>();
+      return true;
     case WN_TARGET_STOCK_WATSON: {
       // d = 3T; thread t owns B consecutive time steps: T <= G*B
       if (c.d % 3 != 0) return false;
@@ -164,6 +169,20 @@ __global__ void moments_kernel(const double* __restrict__ state, int n_chains, i
   }
   mean[j] = m;
   var[j] = n_chains > 1 ? ss / (n_chains - 1) : 0.0;
+}
+
+__global__ void transpose_kernel(const double* __restrict__ X, double* __restrict__ XT, int N, int P) {
+  __shared__ double tile[32][33];
+  const int n0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int n = n0 + i, k = k0 + threadIdx.x;
+    tile[i][threadIdx.x] = (n < N && k < P) ? X[(size_t)n * P + k] : 0.0;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int k = k0 + i, n = n0 + threadIdx.x;
+    if (k < P && n < N) XT[(size_t)k * N + n] = tile[threadIdx.x][i];
+  }
 }
 
 __global__ void fp64_fma_kernel(double* out, int iters, double a, double b) {
@@ -238,7 +257,7 @@ void wn_destroy(wn_handle* h) {
     cudaStreamSynchronize(h->stream);
   }
   cudaFree(h->d_state); cudaFree(h->d_scratch); cudaFree(h->d_queue); cudaFree(h->d_totals);
-  cudaFree(h->d_p0); cudaFree(h->d_p1); cudaFree(h->d_inv_mass); cudaFree(h->d_H); cudaFree(h->d_delta);
+  cudaFree(h->d_p0); cudaFree(h->d_p1); cudaFree(h->d_p2); cudaFree(h->d_inv_mass); cudaFree(h->d_H); cudaFree(h->d_delta);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -275,7 +294,18 @@ int wn_set_data(wn_handle* h, const char* key, const double* ptr, int64_t n, int
     if (n != c.n_chains) return fail(h, WN_EINVAL, "delta must have n_chains entries");
     return upload(h, &h->d_delta, ptr, n, on_device);
   }
-  if (!strcmp(key, "X")) { h->n_p0 = n; return upload(h, &h->d_p0, ptr, n, on_device); }
+  if (!strcmp(key, "X")) {
+    if (n % c.d != 0) return fail(h, WN_EINVAL, "X must have N*d entries (row-major [N, d])");
+    const int N = (int)(n / c.d);
+    int rc = upload(h, &h->d_p0, ptr, n, on_device);
+    if (rc) return rc;
+    h->n_p0 = N;
+    if (h->d_p2) { cudaFree(h->d_p2); h->d_p2 = nullptr; }
+    CUDA_TRY(h, cudaMalloc(&h->d_p2, (size_t)n * sizeof(double)));
+    transpose_kernel<<<dim3((N + 31) / 32, (c.d + 31) / 32), dim3(32, 8), 0, h->stream>>>(h->d_p0, h->d_p2, N, c.d);
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return WN_OK;
+  }
   if (!strcmp(key, "y")) {
     if (c.target == WN_TARGET_STOCK_WATSON) { h->n_p0 = n; return upload(h, &h->d_p0, ptr, n, on_device); }
     h->n_p1 = n;
@@ -318,6 +348,8 @@ int wn_run_async(wn_handle* h, int64_t n_iter, double* d_draws, double* d_diag, 
   if (!h->have_state) return fail(h, WN_ESTATE, "wn_run before wn_set_state");
   const wn_config& c = h->cfg;
   if (c.target == WN_TARGET_DIAG_GAUSS && !h->d_p0) return fail(h, WN_ESTATE, "diag_gauss needs data key inv_var");
+  if (c.target == WN_TARGET_LOGREG && (!h->d_p0 || !h->d_p1 || h->n_p1 != h->n_p0))
+    return fail(h, WN_ESTATE, "logreg needs data keys X [N*d] and y [N]");
   if (c.target == WN_TARGET_STOCK_WATSON && (!h->d_p0 || h->n_p0 * 3 != c.d))
     return fail(h, WN_ESTATE, "stock_watson needs data key y with T = d/3 entries");
   if (c.mode == WN_MODE_PACKAGE && !h->d_inv_mass) return fail(h, WN_ESTATE, "package mode needs data key inv_mass");
@@ -346,7 +378,7 @@ int wn_run_async(wn_handle* h, int64_t n_iter, double* d_draws, double* d_diag, 
   CUDA_TRY(h, cudaMemsetAsync(h->d_totals, 0, 2 * sizeof(unsigned long long), h->stream));
 
   TargetParams tp;
-  tp.p0 = h->d_p0; tp.p1 = h->d_p1; tp.n0 = (int)h->n_p0; tp.n1 = (int)h->n_p1;
+  tp.p0 = h->d_p0; tp.p1 = h->d_p1; tp.p2 = h->d_p2; tp.n0 = (int)h->n_p0; tp.n1 = (int)h->n_p1;
   tp.c0 = 1.0 / (h->tau * h->tau);
 
   CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));

@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(NT, MINB) package_kernel(const __grid_constant
   enum { V_PARK_Q = 0, V_PARK_V = 1, V_PARK_G = 2, V_PROP0 = 3, V_PROP1 = 4, V_STACK = 5 };
 
   Target target;
-  target.init(P.tp, P.d, t);
+  target.init(P.tp, P.d, t, red + 2 * ((G + 31) / 32) * 8);
 
   double q[E], v[E], g[E], im[E], sim[E];
 #pragma unroll
@@ -178,6 +178,9 @@ __global__ void __launch_bounds__(NT, MINB) package_kernel(const __grid_constant
 
   int st = PS_CHAIN;
   for (;;) {
+    if constexpr (Target::BLOCK_LOCKSTEP) {
+      if (__syncthreads_and(st == PS_EXIT)) break;
+    }
     // =============================== hot: one micro-step ========================================
     if (st == PS_RUN) {
       // drift, gradient, kick (:170-175 stable_steps, :91-94 leapfrog)
@@ -505,7 +508,10 @@ __global__ void __launch_bounds__(NT, MINB) package_kernel(const __grid_constant
           break;
       }
     }
-    if (st == PS_EXIT) break;
+    if (st == PS_EXIT) {
+      if constexpr (Target::BLOCK_LOCKSTEP) continue;
+      break;
+    }
   }
   if (t == 0 && tot) atomicAdd(P.totals, tot);
 }

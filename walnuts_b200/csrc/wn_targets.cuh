@@ -13,6 +13,7 @@ namespace wn {
 struct TargetParams {
   const double* p0;  // inv_var [d]      | X [N,P] row-major | y [T]
   const double* p1;  // -                | y [N]             | -
+  const double* p2;  // -                | X^T [P,N]         | -
   int n0, n1;        // -                | N, P              | T
   double c0;         // -                | 1/tau^2           | -
 };
@@ -30,9 +31,11 @@ template <int G, int E2, bool UNIT>
 struct DiagGaussT {
   static constexpr int E = 2 * E2;
   static constexpr bool PAIR_LAYOUT = true;
+  static constexpr bool BLOCK_LOCKSTEP = false;
+  __host__ __device__ static constexpr int smem_doubles(int) { return 0; }
   __device__ __forceinline__ int coord(int e, int t) const { return coord_of<G>(e, t); }
   double s[UNIT ? 1 : E];
-  __device__ __forceinline__ void init(const TargetParams& tp, int d, int t) {
+  __device__ __forceinline__ void init(const TargetParams& tp, int d, int t, double*) {
     if constexpr (!UNIT) {
 #pragma unroll
       for (int e = 0; e < E; ++e) {
@@ -60,11 +63,13 @@ template <int G, int E2>
 struct FunnelT {
   static constexpr int E = 2 * E2;
   static constexpr bool PAIR_LAYOUT = true;
+  static constexpr bool BLOCK_LOCKSTEP = false;
+  __host__ __device__ static constexpr int smem_doubles(int) { return 0; }
   __device__ __forceinline__ int coord(int e, int t) const { return coord_of<G>(e, t); }
   static_assert(G <= 32, "funnel target needs the chain inside one warp");
   int d_;
   double nn;
-  __device__ __forceinline__ void init(const TargetParams&, int d, int) {
+  __device__ __forceinline__ void init(const TargetParams&, int d, int, double*) {
     d_ = d;
     nn = (double)(d - 1);
   }
@@ -101,10 +106,12 @@ template <int G, int E2>
 struct FunnelPkgT {
   static constexpr int E = 2 * E2;
   static constexpr bool PAIR_LAYOUT = true;
+  static constexpr bool BLOCK_LOCKSTEP = false;
+  __host__ __device__ static constexpr int smem_doubles(int) { return 0; }
   __device__ __forceinline__ int coord(int e, int t) const { return coord_of<G>(e, t); }
   static_assert(G <= 32, "funnel target needs the chain inside one warp");
   int d_;
-  __device__ __forceinline__ void init(const TargetParams&, int d, int) { d_ = d; }
+  __device__ __forceinline__ void init(const TargetParams&, int d, int, double*) { d_ = d; }
   __device__ __forceinline__ double lp_grad(const double (&q)[E], double (&g)[E], double* red, int& parity) const {
     const int t = threadIdx.x & (G - 1);
     double x[1] = {0.0};
@@ -135,9 +142,11 @@ template <int G, int E2>
 struct CorrGaussT {
   static constexpr int E = 2 * E2;
   static constexpr bool PAIR_LAYOUT = true;
+  static constexpr bool BLOCK_LOCKSTEP = false;
+  __host__ __device__ static constexpr int smem_doubles(int) { return 0; }
   __device__ __forceinline__ int coord(int e, int t) const { return coord_of<G>(e, t); }
   static_assert(G == 1 && E2 == 1, "corr_gauss is 2-d");
-  __device__ __forceinline__ void init(const TargetParams&, int, int) {}
+  __device__ __forceinline__ void init(const TargetParams&, int, int, double*) {}
   __device__ __forceinline__ double lp_grad(const double (&q)[E], double (&g)[E], double*, int&) const {
     const double rho = 0.5, tmp = 1.0 - rho * rho;
     const double r = q[1] - rho * q[0];
@@ -165,13 +174,15 @@ struct StockWatsonT {
   static constexpr int E = 2 * E2;
   static constexpr int B = (E - 2) / 3;
   static constexpr bool PAIR_LAYOUT = false;
+  static constexpr bool BLOCK_LOCKSTEP = false;
+  __host__ __device__ static constexpr int smem_doubles(int) { return 0; }
   static constexpr int WARPS = (G + 31) / 32;
   static_assert(3 * B + 2 == E, "E must be 3B + 2");
   static_assert(G % 32 == 0, "Stock-Watson target needs whole warps per chain");
   int T;
   double y[B];
 
-  __device__ __forceinline__ void init(const TargetParams& tp, int, int t) {
+  __device__ __forceinline__ void init(const TargetParams& tp, int, int t, double*) {
     T = tp.n0;
 #pragma unroll
     for (int i = 0; i < B; ++i) {
@@ -328,6 +339,108 @@ struct StockWatsonT {
     g[3 * B + 1] = 0.0;
     if (t == 0) lp += 5.0 * tS - 0.5 * etS;
     return lp;
+  }
+};
+
+}  // namespace wn
+
+namespace wn {
+
+// ---- T4: Bayesian logistic regression (not in the reference) -----------------------
+// lp = sum_n [y_n eta_n - log(1 + exp(eta_n))] - |beta|^2 / (2 tau^2),  eta = X beta,
+// grad = X^T (y - sigmoid(eta)) - beta / tau^2;  X [N,P] row-major plus its transpose X^T [P,N].
+// One warp per chain (G = 32, P <= 64*E2).  Rows are processed in tiles of RT: phase 1 computes
+// eta / residuals with one lane per row (X^T: coalesced over rows, beta broadcast from shared memory),
+// phase 2 accumulates X^T r with one lane per coordinate pair (X: coalesced over coordinates, residuals
+// broadcast).  The warps of a block run their evaluations in lock-step (one barrier per trip of the
+// sampler's loop), so that the X tiles one warp pulls into L1 are reused by the block's other chains.
+template <int G, int E2>
+struct LogRegT {
+  static constexpr int E = 2 * E2;
+  static constexpr bool PAIR_LAYOUT = true;
+  static constexpr bool BLOCK_LOCKSTEP = true;
+  static constexpr int RT = 128, RJ = RT / 32, PMAX = 2 * G * E2;
+  static_assert(G == 32, "logistic regression target: one warp per chain");
+  __host__ __device__ static constexpr int smem_doubles(int NT) { return (NT / 32) * (PMAX + RT); }
+  const double *X, *XT, *y;
+  int N, P;
+  double itau2;
+  double *bs, *rs;
+  __device__ __forceinline__ int coord(int e, int t) const { return coord_of<G>(e, t); }
+  __device__ __forceinline__ void init(const TargetParams& tp, int d, int, double* tsm) {
+    X = tp.p0; y = tp.p1; XT = tp.p2; N = tp.n0; P = d; itau2 = tp.c0;
+    bs = tsm + (threadIdx.x >> 5) * (PMAX + RT);
+    rs = bs + PMAX;
+  }
+  __device__ __forceinline__ double lp_grad(const double (&q)[E], double (&g)[E], double*, int&) const {
+    const int t = threadIdx.x & 31;
+    __syncwarp();
+#pragma unroll
+    for (int e = 0; e < E; ++e) bs[coord_of<G>(e, t)] = q[e];
+    __syncwarp();
+    double lp = 0.0;
+    double acc[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) acc[e] = 0.0;
+    for (int n0 = 0; n0 < N; n0 += RT) {
+      // phase 1: eta for rows n0 + t + 32 j
+      double eta[RJ];
+#pragma unroll
+      for (int j = 0; j < RJ; ++j) eta[j] = 0.0;
+      if (n0 + RT <= N) {
+#pragma unroll 4
+        for (int k = 0; k < P; ++k) {
+          const double b = bs[k];
+          const double* col = XT + (size_t)k * N + n0 + t;
+#pragma unroll
+          for (int j = 0; j < RJ; ++j) eta[j] = fma(__ldg(col + 32 * j), b, eta[j]);
+        }
+      } else {
+        for (int k = 0; k < P; ++k) {
+          const double b = bs[k];
+          const double* col = XT + (size_t)k * N + n0 + t;
+#pragma unroll
+          for (int j = 0; j < RJ; ++j)
+            if (n0 + t + 32 * j < N) eta[j] = fma(__ldg(col + 32 * j), b, eta[j]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < RJ; ++j) {
+        const int n = n0 + t + 32 * j;
+        double r = 0.0;
+        if (n < N) {
+          const double yy = __ldg(y + n), et = eta[j];
+          const double ex = exp(-fabs(et));
+          const double inv = 1.0 / (1.0 + ex);
+          const double sig = (et >= 0.0) ? inv : ex * inv;
+          r = yy - sig;
+          lp += yy * et - (fmax(et, 0.0) + log1p(ex));
+        }
+        rs[t + 32 * j] = r;
+      }
+      __syncwarp();
+      // phase 2: acc_k += X[n][k] * r_n for this lane's coordinates
+      const int nend = min(RT, N - n0);
+#pragma unroll 4
+      for (int i = 0; i < nend; ++i) {
+        const double r = rs[i];
+        const double* row = X + (size_t)(n0 + i) * P;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          const int k = coord_of<G>(e, t);
+          if (k < P) acc[e] = fma(__ldg(row + k), r, acc[e]);
+        }
+      }
+      __syncwarp();
+    }
+    double qq = 0.0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int k = coord_of<G>(e, t);
+      g[e] = (k < P) ? fma(-itau2, q[e], acc[e]) : 0.0;
+      qq = fma(q[e], q[e], qq);
+    }
+    return lp - 0.5 * itau2 * qq;
   }
 };
 

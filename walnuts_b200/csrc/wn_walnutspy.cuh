@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
   };
 
   Target target;
-  target.init(P.tp, P.d, t);
+  target.init(P.tp, P.d, t, red + 2 * ((G + 31) / 32) * 8);
 
   // ---- register-resident working state -----------------------------------------------------
   double q[E], v[E], g[E];
@@ -179,6 +179,11 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
 
   int st = ST_CHAIN;
   for (;;) {
+    if constexpr (Target::BLOCK_LOCKSTEP) {
+      // chains of a block evaluate their gradients in lock-step (shared data tiles stay hot in L1);
+      // the same barrier doubles as the block's exit vote
+      if (__syncthreads_and(st == ST_EXIT)) break;
+    }
     // =============================== hot: leapfrog micro-steps ==================================
     if (st == ST_RUN) {
       if (steps_left >= 2u) {   // two steps per trip: the tail of one overlaps the head of the next
@@ -618,7 +623,10 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
           break;
       }
     }
-    if (st == ST_EXIT) break;
+    if (st == ST_EXIT) {
+      if constexpr (Target::BLOCK_LOCKSTEP) continue;
+      break;
+    }
   }
   if (t == 0 && (totF | totB)) {
     atomicAdd(P.totals, totF);

@@ -50,6 +50,16 @@ def stock_watson(y):
     return Target("stock_watson", data={"y": y}, d=3 * y.size, ref="sw_innov.stan:2-52")
 
 
+def logreg(X, y, tau=1.0):
+    """Bayesian logistic regression: Bernoulli-logit likelihood for rows of X [N, P]
+    with responses y in {0, 1} and a N(0, tau^2 I) prior on the P coefficients."""
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    if X.ndim != 2 or y.shape != (X.shape[0],):
+        raise ValueError("X must be [N, P] and y [N]")
+    return Target("logreg", data={"X": X, "y": y, "tau": np.array([float(tau)])}, d=X.shape[1], ref="SURVEY.md T4")
+
+
 def resolve(target, d):
     """Target handle (or registry name) -> (name, data) after checking the dimension."""
     if isinstance(target, str):
