@@ -32,7 +32,11 @@ sys.path.insert(0, ROOT)
 D = 1000
 CHAINS_PER_GPU = 65536
 CFG = dict(integrator="R2P", H0=0.5, delta=0.3, M=10, minC=0, maxC=10, jitter=0.2)
-FLOP_PER_DIM_PER_EVAL = 12        # leapfrog + gradient + energy, diag Gaussian
+# Algorithmic FP64 work per gradient evaluation and coordinate: v+=a*g, q+=h*v, g=-q*s, v+=a*g = 4 FP64
+# instructions = 8 flop (7 strictly; an FMA counts 2).  SURVEY.md section 8(d) quotes 12 flop including the
+# per-step energy (2 more FMAs); the kernel evaluates energies only where the algorithm consumes them (last
+# step of each pass), so the conservative 8 is used as numerator -- see DESIGN.md section 6.
+FLOP_PER_DIM_PER_EVAL = 8
 SEED = 20251017
 MONITOR = 16                      # coordinates monitored for ESS (spread over the sigma range)
 

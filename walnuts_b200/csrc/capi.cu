@@ -120,12 +120,14 @@ static bool pick_plan(const wn_config& c, LaunchPlan& p) {
   switch (c.target) {
     case WN_TARGET_STD_NORMAL: return pick_generic<StdNormalT>(pkg, c.d, p);
     case WN_TARGET_DIAG_GAUSS: {
-      const char* v = getenv("WN_VARIANT");   // tuning experiments only
-      if (v && !pkg && c.d > 512 && c.d <= 1024) {
-        switch (atoi(v)) {
-          case 1: p = plan_wpy<DiagT, 128, 4, 128, 3>(); return true;
-          case 2: p = plan_wpy<DiagT, 128, 4, 128, 4>(); return true;
-          default: break;
+      if (!pkg && c.d > 512 && c.d <= 1024) {
+        // BASELINE config 2 (d = 1000): 128 threads x 8 coordinates, 4 blocks / SM (128 registers);
+        // WN_VARIANT selects the alternatives measured in DESIGN.md section 6 (tuning only)
+        const char* v = getenv("WN_VARIANT");
+        switch (v ? atoi(v) : 0) {
+          case 1: p = plan_wpy<DiagT, 64, 8, 64, 1>(); return true;
+          case 2: p = plan_wpy<DiagT, 128, 4, 128, 3>(); return true;
+          default: p = plan_wpy<DiagT, 128, 4, 128, 4>(); return true;
         }
       }
       return pick_generic<DiagT>(pkg, c.d, p);

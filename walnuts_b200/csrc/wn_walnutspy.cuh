@@ -104,6 +104,14 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
   uint32_t steps_left = 0;
   double hh = 0, ha = 0, hp = 0;
   int expmax = 0;          // max over the pass of the exponent field of the per-thread energy partial
+  int smax = 0;            // lazy-energy passes: signed / unsigned max of the high words of q, v
+  unsigned umax = 0;
+  bool lazy = false;       // current pass skips intermediate energies
+  // register copy of the step-size search state: a failed attempt goes straight to the next one
+  int rc = 0, rlim = 0;
+  bool rsearch = false, rexact = false, rlazyok = false;
+  double rh = 0, rHref = 0, rdelta = 0, rsign = 1.0;
+  unsigned long long rEv = 0;
   unsigned long long totF = 0, totB = 0;
 
   auto useq = [&]() -> double {
@@ -132,11 +140,25 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
       g[e] = ck[(2 * E + e) * NT + tid];
     }
   };
+  auto track_state = [&]() {
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int hq = __double2hiint(q[e]), hv = __double2hiint(v[e]);
+      smax = max(smax, max(hq, hv));
+      umax = max(umax, max((unsigned)hq, (unsigned)hv));
+    }
+  };
   auto start_pass = [&](int cc) {
     steps_left = 1u << cc;
-    hh = ldexp(C.h, -cc);
+    hh = ldexp(rh, -cc);
     ha = 0.5 * hh;
     expmax = 0;
+    smax = 0;
+    umax = 0;
+    if constexpr (Target::LAZY_ENERGY) {
+      lazy = rlazyok && !rexact && (cc >= 2);
+      if (lazy) track_state();   // the pass starts from a bounded state
+    }
   };
   // U-turn criterion, reference WALNUTS.py:95-97; (ql, vl) read from scratch, the other state is the
   // register-resident end (q, xi*v).  Orientation: minus end = more backward state.
@@ -176,6 +198,25 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
     // all(isfinite(Hams)) (:92) is tracked on the exponent field with integer ops, off the FP64 pipe
     expmax = max(expmax, __double2hiint(hp) & 0x7ff00000);
   };
+  // The same step without the energy (targets with LAZY_ENERGY).  Instead, the magnitudes of q and v
+  // are bounded: the high words are max-reduced as signed ints (largest positive value) and as
+  // unsigned ints (largest-magnitude negative value) -- two 3-input integer max per coordinate, off the
+  // FP64 pipe -- at the pass start and after every second skipped step.  With inv_var <= 2^60 and a
+  // micro step <= 2^10 one leapfrog step amplifies |q|, |v| by at most 2^142, so "checked states below
+  // 2^300" implies every state in between is below 2^442 and every skipped energy is finite.
+  auto micro_step_lazy = [&]() {
+    if constexpr (Target::LAZY_ENERGY) {
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        v[e] = fma(ha, g[e], v[e]);
+        q[e] = fma(hh, v[e], q[e]);
+      }
+      target.grad_only(q, g);
+#pragma unroll
+      for (int e = 0; e < E; ++e) v[e] = fma(ha, g[e], v[e]);
+    }
+  };
+  constexpr int LAZY_LIMIT = (1023 + 300) << 20;
 
   int st = ST_CHAIN;
   for (;;) {
@@ -186,7 +227,16 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
     }
     // =============================== hot: leapfrog micro-steps ==================================
     if (st == ST_RUN) {
-      if (steps_left >= 2u) {   // two steps per trip: the tail of one overlaps the head of the next
+      if (Target::LAZY_ENERGY && lazy && steps_left >= 3u) {
+        micro_step_lazy();
+        micro_step_lazy();
+        track_state();
+        steps_left -= 2u;
+      } else if (Target::LAZY_ENERGY && lazy && steps_left == 2u) {
+        micro_step_lazy();
+        micro_step();
+        steps_left = 0u;
+      } else if (steps_left >= 2u) {   // two steps per trip: the tail of one overlaps the head of the next
         micro_step();
         micro_step();
         steps_left -= 2u;
@@ -343,10 +393,16 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
             h = C.h2;
           }
           C.h = h;
-          C.Ham0 = C.side ? C.endH1 : C.endH0;
+          const double Ham0 = C.side ? C.endH1 : C.endH0;
+          C.Ham0 = Ham0;
           C.phase = PH_FWD;
           const int c0 = (P.kind == KIND_FIXED) ? 0 : P.minC;
           C.c = c0;
+          rh = h; rc = c0; rlim = P.maxC; rHref = Ham0; rdelta = C.delta; rsign = 1.0;
+          rsearch = (P.kind != KIND_FIXED);
+          rexact = false;
+          rEv = 0;
+          if constexpr (Target::LAZY_ENERGY) rlazyok = target.lazy_ok && (C.jhi <= 1024.0);
           if (P.kind != KIND_FIXED) save_ck();   // S = start state (integration convention)
           C.wIntact = 1;
           start_pass(c0);
@@ -354,18 +410,49 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
           break;
         }
         case ST_PASS_END: {  // a pass of 2^c micro-steps finished
-          double x[2] = {hp, (expmax == 0x7ff00000) ? 1.0 : 0.0};
+          const bool unbounded = (smax & 0x7ff00000) >= LAZY_LIMIT ||
+                                 ((umax & 0x80000000u) && (int)(umax & 0x7ff00000u) >= LAZY_LIMIT);
+          double x[2] = {hp, ((expmax == 0x7ff00000) ? 1.0 : 0.0) + (unbounded ? 1024.0 : 0.0)};
           Grp::template sum<2>(x, red, parity);
           const double Hend = x[0];
+          const bool redo_exact = Target::LAZY_ENERGY && x[1] >= 1024.0;
           const bool anybad = x[1] != 0.0;
+          if (rsearch && !redo_exact) {
+            // fast path of the search (adaptiveIntegrators.py:69-94, 111-132): attempt failed -> next c
+            const bool ok = !anybad && fabs(rHref - Hend) < rdelta;
+            if (!ok && rc < rlim) {
+              rEv += 1ull << rc;
+              ++rc;
+              rexact = false;
+              load_ck(rsign);
+              start_pass(rc);
+              st = ST_RUN;
+              break;
+            }
+          }
           const int phase = C.phase;
+          if (rsearch) {   // leave the fast path: write the search state back
+            C.c = rc;
+            if (phase == PH_FWD) C.nF = C.nF + rEv; else C.nB = C.nB + rEv;
+            rEv = 0;
+          }
           int c = C.c;
+          if (redo_exact) {
+            // a skipped energy might have been non-finite: repeat this pass with per-step energies
+            rexact = true;
+            load_ck(phase == PH_BWD ? -1.0 : 1.0);
+            start_pass(phase == PH_REDO ? C.cSim : c);
+            st = ST_RUN;
+            break;
+          }
+          rexact = false;
           if (phase == PH_FWD) {
             C.nF = C.nF + (1ull << c);
             const bool ok = !anybad && fabs(C.Ham0 - Hend) < C.delta;   // adaptiveIntegrators.py:87-92
             if (!(P.kind == KIND_FIXED || ok || c == P.maxC)) {
               ++c;
               C.c = c;
+              rc = c;
               load_ck(1.0);
               start_pass(c);
               st = ST_RUN;
@@ -380,6 +467,7 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
               } else {                          // :400-424 redo at If+1
                 C.cSim = c + 1;
                 C.phase = PH_REDO;
+                rsearch = false;
                 load_ck(1.0);
                 start_pass(c + 1);
                 st = ST_RUN;
@@ -410,6 +498,7 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
               C.wIntact = 0;
               C.phase = PH_BWD;
               C.c = P.minC;
+              rc = P.minC; rlim = maxTry; rHref = Hend; rsign = -1.0; rsearch = true; rEv = 0;
 #pragma unroll
               for (int e = 0; e < E; ++e) v[e] = -v[e];
               start_pass(P.minC);
@@ -423,6 +512,7 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
             if (!ok && c < C.maxTry) {
               ++c;
               C.c = c;
+              rc = c;
               load_ck(-1.0);
               start_pass(c);
               st = ST_RUN;
