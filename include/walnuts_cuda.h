@@ -99,6 +99,14 @@ void wn_destroy(wn_handle* h);
  * `on_device` != 0: `ptr` is a device pointer on cfg.device. */
 int wn_set_data(wn_handle* h, const char* key, const double* ptr, int64_t n, int on_device);
 
+/* Warm-up adaptation of the macro step H and the tolerance delta, per chain, as reference
+ * WALNUTS.py:136-147 (setup), :313 (P-squared quantile of log igrConst, P2quantile.py:16-92) and
+ * :701-712 (delta <- target / quantile(orbitEnergyError/delta), H <- delta^(1/3) exp(P2 quantile)).
+ * Iterations 1..warmup_iter of the handle adapt; later ones use the adapted values.  Must be called
+ * before the first wn_run.  WALNUTSPY mode only. */
+int wn_set_adapt(wn_handle* h, int64_t warmup_iter, int adaptH, double adaptHtarget, int adaptDelta,
+                 double adaptDeltaTarget, double adaptDeltaQuantile);
+
 /* Positions of all chains, row-major [n_chains, d]. */
 int wn_set_state(wn_handle* h, const double* q, int on_device);
 int wn_get_state(wn_handle* h, double* q, int on_device);

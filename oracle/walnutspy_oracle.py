@@ -288,6 +288,59 @@ def transition(lpFun, qc, rng, kind, H, delta, M, aux, jitter=0.2, igr_sink=None
     return qProp, diag
 
 
+class P2Quantile:
+    """Restatement of WALNUTSpy/P2quantile.py:16-92 (P-squared online quantile, Jain & Chlamtac 1985),
+    including its behaviour when `findInterval` falls through (xi == q[4]: :31-39 returns None, and
+    `n[None:5] += 1` then increments every marker position)."""
+
+    def __init__(self, prob=0.5):
+        self.npush = 0
+        self.p = prob
+        self.q = np.zeros(5)
+        self.n = np.arange(1, 6)
+
+    def quantile(self):
+        return self.q[2]
+
+    def push(self, xi):
+        self.npush += 1
+        if self.npush <= 5:
+            self.q[self.npush - 1] = xi
+            if self.npush == 5:
+                self.q = np.sort(self.q)                    # :45-47
+            return
+        q, n = self.q, self.n
+        if xi < q[0]:                                        # :31-39, 49-57
+            q[0] = xi
+            k = 1
+        elif xi > q[4]:
+            q[4] = xi
+            k = 4
+        else:
+            k = None
+            for i in range(4):
+                if xi < q[i + 1]:
+                    k = i + 1
+                    break
+        n[k:5] += 1                                          # :60
+        nn, pp = self.npush, self.p
+        npp = np.array([1.0, 0.5 * (nn - 1) * pp + 1.0, (nn - 1) * pp + 1.0, (nn - 1) * (1 + pp) / 2.0 + 1, nn])
+        with np.errstate(all="ignore"):
+            for i in range(2, 5):                            # :70-89
+                ni, nip, nim = n[i - 1], n[i], n[i - 2]
+                di = npp[i - 1] - ni
+                if (di >= 1.0 and nip - ni > 1) or (di <= -1.0 and nim - ni < -1):
+                    di = np.sign(di).astype(np.int64)
+                    qi = q[i - 1]
+                    qip = qi + (di / (nip - nim)) * ((ni - nim + di) * (q[i] - qi) / (nip - ni)
+                                                     + (nip - ni - di) * (qi - q[i - 2]) / (ni - nim))
+                    if q[i - 2] < qip and qip < q[i]:
+                        q[i - 1] = qip
+                    else:
+                        q[i - 1] = qi + di * (q[i + di - 1] - qi) / (n[i + di - 1] - n[i - 1])
+                    n[i - 1] += di
+
+
 class PhiloxRNG:
     """Adapter: oracle.philox.ChainStreams -> the rng protocol used by transition()."""
 
@@ -325,8 +378,9 @@ class NumpyGlobalRNG:
 
 def WALNUTS(lpFun, q0, generated=lambda q: q, integrator=FIXED, H0=0.2, stepSizeRandScale=0.2,
             delta0=0.05, numIter=2000, M=10, igrAux=None, rng=None, seed=0, chain=0,
-            first_iteration=1):
-    """Fixed-(H, delta) WALNUTSpy chain (warmupIter=0, adaptH=adaptDelta=False).
+            first_iteration=1, warmupIter=0, adaptH=False, adaptHtarget=0.8, adaptDelta=False,
+            adaptDeltaTarget=0.6, adaptDeltaQuantile=0.9):
+    """WALNUTSpy chain incl. the warm-up adaptation of H and delta (WALNUTS.py:136-147, 313, 701-712).
     Returns (samples (dg, numIter+1), diagnostics (numIter, 24)) like WALNUTS.py:724-727."""
     from . import philox
     aux = igrAux or AuxPar()
@@ -339,10 +393,26 @@ def WALNUTS(lpFun, q0, generated=lambda q: q, integrator=FIXED, H0=0.2, stepSize
     samples = np.zeros((g0.size, numIter + 1))
     samples[:, 0] = g0
     diagnostics = np.zeros((numIter, 24))
+    H, delta = H0, delta0
+    p2 = P2Quantile(1.0 - adaptHtarget) if adaptH else None                    # :139-141
+    facs = np.zeros(warmupIter) if adaptDelta else None                         # :145-147
     for it in range(1, numIter + 1):
         if streams is not None:
             streams.begin_iteration(first_iteration + it - 1)
-        qc, diagnostics[it - 1] = transition(lpFun, qc, rng, integrator, H0, delta0, M, aux,
-                                             jitter=stepSizeRandScale)
-        samples[:, it] = generated(qc)
+        warmup = it <= warmupIter                                               # :209
+        sink = None
+        if warmup and adaptH:
+            with np.errstate(all="ignore"):
+                sink = lambda c: p2.push(np.log(c))                             # :313
+        with np.errstate(all="ignore"):
+            qc, diagnostics[it - 1] = transition(lpFun, qc, rng, integrator, H, delta, M, aux,
+                                                 jitter=stepSizeRandScale, igr_sink=sink)
+            samples[:, it] = generated(qc)
+            if warmup:                                                          # :701-712
+                if adaptDelta:
+                    facs[it - 1] = diagnostics[it - 1, 17] / delta
+                if adaptDelta and it > 10:
+                    delta = adaptDeltaTarget / np.quantile(facs[0:it], adaptDeltaQuantile)
+                if adaptH and p2.npush > 10:
+                    H = (delta ** (1.0 / 3.0)) * np.exp(p2.quantile())
     return samples, diagnostics

@@ -1,0 +1,66 @@
+"""GPU parity of the warm-up adaptation (reference WALNUTS.py:136-147, 313, 701-712 + P2quantile.py):
+the drop-in WALNUTS(...) call with the reference's DEFAULT arguments (adaptH=True, adaptDelta=True)
+against the numpy oracle, which is pinned bit-exact to the real reference (tests/test_oracle_golden.py)."""
+import numpy as np
+import pytest
+
+from oracle import targets as ot
+from oracle import walnutspy_oracle as wo
+from tests.helpers import KIND, close
+
+pytestmark = pytest.mark.gpu
+
+
+def run_pair(target_name, lp, q0, integrator, numIter, warmupIter, M, seed=77, **kw):
+    import walnuts_b200 as wb
+    tg = {"std_normal": wb.targets.stdGauss, "corr_gauss": wb.targets.corrGauss, "funnel": wb.targets.funnel10}[target_name]
+    ig = {"fixed": wb.fixedLeapFrog, "D": wb.adaptLeapFrogD, "R2P": wb.adaptLeapFrogR2P}[integrator]
+    s, d = wb.WALNUTS(tg, q0, integrator=ig, numIter=numIter, warmupIter=warmupIter, M=M, seed=seed, **kw)
+    n_chains = q0.shape[0]
+    so = np.empty_like(s)
+    do = np.empty_like(d)
+    for c in range(n_chains):
+        so[c], do[c] = wo.WALNUTS(lp, q0[c], integrator=KIND[integrator], numIter=numIter, warmupIter=warmupIter, M=M,
+                                  seed=seed, chain=c, adaptH=kw.get("adaptH", True), adaptDelta=kw.get("adaptDelta", True),
+                                  H0=kw.get("H0", 0.2), delta0=kw.get("delta0", 0.05))
+    return s, d, so, do
+
+
+@pytest.mark.parametrize("integrator", ["fixed", "D", "R2P"])
+@pytest.mark.parametrize("target", ["std_normal", "corr_gauss"])
+def test_default_adaptation_matches_oracle(cuda_lib, target, integrator):
+    d = 6 if target == "std_normal" else 2
+    lp = ot.std_normal if target == "std_normal" else ot.corr_gauss
+    q0 = 0.5 * np.random.default_rng(2).standard_normal((4, d))
+    s, dg, so, do = run_pair(target, lp, q0, integrator, numIter=120, warmupIter=80, M=8)
+    ok, err = close(s, so)
+    assert ok, f"draws: {err:.3e}"
+    ok, err = close(dg[..., [15, 18]], do[..., [15, 18]], rtol=1e-9)       # adapted H and delta, every iteration
+    assert ok, f"adapted H / delta: {err:.3e}"
+    assert np.array_equal(dg[..., [0, 1, 6, 7, 19]], do[..., [0, 1, 6, 7, 19]])
+    # adaptation really happened and then froze
+    assert not np.allclose(dg[:, 79, 15], 0.2) and np.array_equal(dg[:, 80, 15], dg[:, -1, 15])
+
+
+def test_adapt_delta_only_and_h_only(cuda_lib):
+    q0 = 0.5 * np.random.default_rng(3).standard_normal((3, 5))
+    for kw in (dict(adaptH=False, adaptDelta=True), dict(adaptH=True, adaptDelta=False)):
+        s, dg, so, do = run_pair("std_normal", ot.std_normal, q0, "R2P", numIter=70, warmupIter=50, M=7, **kw)
+        ok, err = close(s, so)
+        assert ok, (kw, err)
+        ok, err = close(dg[..., [15, 18]], do[..., [15, 18]], rtol=1e-9)
+        assert ok, (kw, err)
+
+
+def test_funnel_adaptation_prefix(cuda_lib):
+    """Chaotic target: free-running agreement is only expected over a prefix (see test_funnel10)."""
+    rng = np.random.default_rng(5)
+    q0 = np.empty((3, 11))
+    q0[:, 0] = rng.standard_normal(3)
+    q0[:, 1:] = np.exp(0.5 * q0[:, :1]) * rng.standard_normal((3, 10))
+    s, dg, so, do = run_pair("funnel", ot.funnel10, q0, "R2P", numIter=40, warmupIter=40, M=9)
+    err = np.max(np.abs(s - so) / np.maximum(1, np.abs(so)), axis=(0, 1))
+    horizon = int(np.argmax(err > 1e-9)) if (err > 1e-9).any() else len(err)
+    assert horizon >= 20, err[:25]
+    ok, e2 = close(dg[:, :15, [15, 18]], do[:, :15, [15, 18]], rtol=1e-7)
+    assert ok, e2

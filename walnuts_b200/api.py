@@ -34,10 +34,6 @@ def WALNUTS(lpFun, q0, generated=None, integrator=_ig.fixedLeapFrog, H0=0.2, ste
         raise ValueError("bad adaptHtarget")          # sys.exit in the reference, WALNUTS.py:140
     if adaptDelta and adaptDeltaTarget < 0.0:
         raise ValueError("bad adaptDeltaTarget")      # WALNUTS.py:146
-    if warmupIter > 0 and (adaptH or adaptDelta):
-        raise NotImplementedError(
-            "warm-up adaptation of H/delta (WALNUTS.py:701-712) is not on the GPU yet (SURVEY.md row N1): "
-            "call with warmupIter=0 or adaptH=False, adaptDelta=False and fixed H0/delta0")
     if recordOrbitStats:
         raise NotImplementedError("recordOrbitStats (WALNUTS.py:182-184) is not implemented (SURVEY.md row N2)")
     if not isinstance(integrator, _ig._Integrator):
@@ -54,8 +50,17 @@ def WALNUTS(lpFun, q0, generated=None, integrator=_ig.fixedLeapFrog, H0=0.2, ste
                     jitter=stepSizeRandScale, delta=delta0, M=M, minC=aux.minC, maxC=aux.maxC,
                     r2p_prob0=aux.R2Pprob0, seed=seed, chain_offset=chain_offset, device=device,
                     data=data) as cb:
+        if warmupIter > 0 and (adaptH or adaptDelta):
+            cb.set_adapt(min(warmupIter, numIter), adaptH, adaptHtarget, adaptDelta, adaptDeltaTarget,
+                         adaptDeltaQuantile)
         cb.set_state(q)
-        out = cb.run(numIter, draws=True, diag=True)
+        nw = min(warmupIter, numIter) if (adaptH or adaptDelta) else 0
+        parts = []
+        if nw > 0:
+            parts.append(cb.run(nw, draws=True, diag=True))          # adapting iterations
+        if numIter - nw > 0:
+            parts.append(cb.run(numIter - nw, draws=True, diag=True))
+        out = {k: np.concatenate([p_[k] for p_ in parts]) for k in ("draws", "diag")}
     draws = out["draws"]                                    # (numIter, n_chains, d)
     gen = generated if generated is not None else (lambda x: x)
     g0 = np.asarray(gen(q[0]))

@@ -28,6 +28,11 @@ struct wn_handle {
   double* d_inv_mass = nullptr;
   double* d_H = nullptr;
   double* d_delta = nullptr;
+  double* d_adapt_state = nullptr;   // warm-up adaptation (wn_set_adapt)
+  double* d_adapt_hist = nullptr;
+  int warmup_iter = 0, adaptH = 0, adaptDelta = 0;
+  bool adapt_exported = false;
+  double adHtarget = 0.8, adTarget = 0.6, adQuant = 0.9;
   int64_t n_p0 = 0, n_p1 = 0;
   double tau = 1.0;
   uint32_t iter_done = 0;
@@ -64,10 +69,10 @@ struct LaunchPlan {
   bool package;
 };
 
-template <template <int, int> class T, int G, int E2, int NT, int MINB = 1>
+template <template <int, int> class T, int G, int E2, int NT, int MINB = 1, bool ADAPT = false>
 static LaunchPlan plan_wpy() {
   LaunchPlan p;
-  p.fn = (const void*)walnutspy_kernel<T, G, E2, NT, MINB>;
+  p.fn = (const void*)walnutspy_kernel<T, G, E2, NT, MINB, ADAPT>;
   p.G = G; p.E2 = E2; p.NT = NT;
   p.smem = (size_t)(3 * 2 * E2 * NT + 2 * ((G + 31) / 32) * 8 + T<G, E2>::smem_doubles(NT)) * sizeof(double);
   p.package = false;
@@ -83,11 +88,19 @@ static LaunchPlan plan_pkg() {
   return p;
 }
 
+// mode: 0 = WALNUTSpy kernel, 1 = package kernel, 2 = WALNUTSpy kernel with warm-up adaptation
+template <template <int, int> class T, int G, int E2, int NT>
+static LaunchPlan plan_for(int mode) {
+  if (mode == 1) return plan_pkg<T, G, E2, NT>();
+  if (mode == 2) return plan_wpy<T, G, E2, NT, 1, true>();
+  return plan_wpy<T, G, E2, NT>();
+}
+
 template <template <int, int> class T>
-static bool pick_generic(bool pkg, int d, LaunchPlan& p) {
+static bool pick_generic(int pkg, int d, LaunchPlan& p) {
 #define WN_PICK(G, E2, NT)                                              \
   if (d <= 2 * (G) * (E2)) {                                            \
-    p = pkg ? plan_pkg<T, G, E2, NT>() : plan_wpy<T, G, E2, NT>();      \
+    p = plan_for<T, G, E2, NT>(pkg);                                    \
     return true;                                                        \
   }
   WN_PICK(1, 2, 128)
@@ -101,10 +114,10 @@ static bool pick_generic(bool pkg, int d, LaunchPlan& p) {
   return false;
 }
 template <template <int, int> class T>
-static bool pick_warp(bool pkg, int d, LaunchPlan& p) {  // targets that need the chain inside one warp
+static bool pick_warp(int pkg, int d, LaunchPlan& p) {  // targets that need the chain inside one warp
 #define WN_PICK(G, E2, NT)                                              \
   if (d <= 2 * (G) * (E2)) {                                            \
-    p = pkg ? plan_pkg<T, G, E2, NT>() : plan_wpy<T, G, E2, NT>();      \
+    p = plan_for<T, G, E2, NT>(pkg);                                    \
     return true;                                                        \
   }
   WN_PICK(1, 6, 128)
@@ -115,12 +128,12 @@ static bool pick_warp(bool pkg, int d, LaunchPlan& p) {  // targets that need th
   return false;
 }
 
-static bool pick_plan(const wn_config& c, LaunchPlan& p) {
-  const bool pkg = c.mode == WN_MODE_PACKAGE;
+static bool pick_plan(const wn_config& c, bool adapt, LaunchPlan& p) {
+  const int pkg = (c.mode == WN_MODE_PACKAGE) ? 1 : (adapt ? 2 : 0);
   switch (c.target) {
     case WN_TARGET_STD_NORMAL: return pick_generic<StdNormalT>(pkg, c.d, p);
     case WN_TARGET_DIAG_GAUSS: {
-      if (!pkg && c.d > 512 && c.d <= 1024) {
+      if (pkg == 0 && c.d > 512 && c.d <= 1024) {
         // BASELINE config 2 (d = 1000): 128 threads x 8 coordinates, 4 blocks / SM (128 registers);
         // WN_VARIANT selects the alternatives measured in DESIGN.md section 6 (tuning only)
         const char* v = getenv("WN_VARIANT");
@@ -136,19 +149,19 @@ static bool pick_plan(const wn_config& c, LaunchPlan& p) {
     case WN_TARGET_FUNNEL_PKG: return pick_warp<FunnelPkgT>(pkg, c.d, p);
     case WN_TARGET_LOGREG:
       if (c.d > 128) return false;
-      p = pkg ? plan_pkg<LogRegT, 32, 2, 256>() : plan_wpy<LogRegT, 32, 2, 256>();
+      p = plan_for<LogRegT, 32, 2, 256>(pkg);
       return true;
     case WN_TARGET_STOCK_WATSON: {
       // d = 3T; thread t owns B consecutive time steps: T <= G*B
       if (c.d % 3 != 0) return false;
       const int T = c.d / 3;
-      if (T <= 64 * 4) { p = pkg ? plan_pkg<StockWatsonT, 64, 7, 64>() : plan_wpy<StockWatsonT, 64, 7, 64>(); return true; }
-      if (T <= 128 * 4) { p = pkg ? plan_pkg<StockWatsonT, 128, 7, 128>() : plan_wpy<StockWatsonT, 128, 7, 128>(); return true; }
+      if (T <= 64 * 4) { p = plan_for<StockWatsonT, 64, 7, 64>(pkg); return true; }
+      if (T <= 128 * 4) { p = plan_for<StockWatsonT, 128, 7, 128>(pkg); return true; }
       return false;
     }
     case WN_TARGET_CORR_GAUSS:
       if (c.d != 2) return false;
-      p = pkg ? plan_pkg<CorrGaussT, 1, 1, 128>() : plan_wpy<CorrGaussT, 1, 1, 128>();
+      p = plan_for<CorrGaussT, 1, 1, 128>(pkg);
       return true;
     default: return false;
   }
@@ -238,7 +251,7 @@ int wn_create(const wn_config* cfg, wn_handle** out) {
   }
   if (c.dg < 0 || c.dg > c.d) return fail(h, WN_EINVAL, "dg must be in [0, d]");
   LaunchPlan p;
-  if (!pick_plan(c, p)) return fail(h, WN_EUNSUPPORTED, "no CUDA kernel for this target/dimension");
+  if (!pick_plan(c, false, p)) return fail(h, WN_EUNSUPPORTED, "no CUDA kernel for this target/dimension");
   CUDA_TRY(h, cudaSetDevice(c.device));
   cudaDeviceProp prop;
   CUDA_TRY(h, cudaGetDeviceProperties(&prop, c.device));
@@ -259,7 +272,7 @@ void wn_destroy(wn_handle* h) {
     cudaStreamSynchronize(h->stream);
   }
   cudaFree(h->d_state); cudaFree(h->d_scratch); cudaFree(h->d_queue); cudaFree(h->d_totals);
-  cudaFree(h->d_p0); cudaFree(h->d_p1); cudaFree(h->d_p2); cudaFree(h->d_inv_mass); cudaFree(h->d_H); cudaFree(h->d_delta);
+  cudaFree(h->d_p0); cudaFree(h->d_p1); cudaFree(h->d_p2); cudaFree(h->d_inv_mass); cudaFree(h->d_H); cudaFree(h->d_delta); cudaFree(h->d_adapt_state); cudaFree(h->d_adapt_hist);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -321,6 +334,41 @@ int wn_set_data(wn_handle* h, const char* key, const double* ptr, int64_t n, int
   return fail(h, WN_EINVAL, std::string("unknown data key ") + key);
 }
 
+int wn_set_adapt(wn_handle* h, int64_t warmup_iter, int adaptH, double adaptHtarget, int adaptDelta,
+                 double adaptDeltaTarget, double adaptDeltaQuantile) {
+  if (!h) return WN_EINVAL;
+  const wn_config& c = h->cfg;
+  if (c.mode != WN_MODE_WALNUTSPY) return fail(h, WN_EINVAL, "warm-up adaptation exists in WALNUTSPY mode only");
+  if (warmup_iter < 0 || warmup_iter > (1 << 24)) return fail(h, WN_EINVAL, "bad warmup_iter");
+  if (adaptH && (adaptHtarget < 0.0 || adaptHtarget > 1.0)) return fail(h, WN_EINVAL, "bad adaptHtarget");        // WALNUTS.py:140
+  if (adaptDelta && adaptDeltaTarget < 0.0) return fail(h, WN_EINVAL, "bad adaptDeltaTarget");                    // WALNUTS.py:146
+  if (adaptDelta && !(adaptDeltaQuantile >= 0.0 && adaptDeltaQuantile <= 1.0)) return fail(h, WN_EINVAL, "bad adaptDeltaQuantile");
+  if (h->iter_done != 0) return fail(h, WN_ESTATE, "wn_set_adapt must precede the first wn_run");
+  CUDA_TRY(h, cudaSetDevice(c.device));
+  cudaFree(h->d_adapt_state); cudaFree(h->d_adapt_hist);
+  h->d_adapt_state = h->d_adapt_hist = nullptr;
+  h->warmup_iter = (int)warmup_iter; h->adaptH = adaptH ? 1 : 0; h->adaptDelta = adaptDelta ? 1 : 0;
+  h->adHtarget = adaptHtarget; h->adTarget = adaptDeltaTarget; h->adQuant = adaptDeltaQuantile;
+  h->adapt_exported = false;
+  if (warmup_iter == 0 || (!adaptH && !adaptDelta)) return WN_OK;
+  std::vector<double> init((size_t)c.n_chains * WN_ADAPT_STRIDE, 0.0), Hs, ds;
+  if (h->d_H) { Hs.resize(c.n_chains); CUDA_TRY(h, cudaMemcpy(Hs.data(), h->d_H, c.n_chains * sizeof(double), cudaMemcpyDeviceToHost)); }
+  if (h->d_delta) { ds.resize(c.n_chains); CUDA_TRY(h, cudaMemcpy(ds.data(), h->d_delta, c.n_chains * sizeof(double), cudaMemcpyDeviceToHost)); }
+  for (int i = 0; i < c.n_chains; ++i) {
+    double* a = &init[(size_t)i * WN_ADAPT_STRIDE];
+    a[0] = Hs.empty() ? c.H0 : Hs[i];
+    a[1] = ds.empty() ? c.delta : ds[i];
+    for (int k = 0; k < 5; ++k) a[8 + k] = k + 1;     // P2quantile.n = 1..5 (P2quantile.py:22)
+  }
+  CUDA_TRY(h, cudaMalloc(&h->d_adapt_state, init.size() * sizeof(double)));
+  CUDA_TRY(h, cudaMemcpy(h->d_adapt_state, init.data(), init.size() * sizeof(double), cudaMemcpyHostToDevice));
+  if (adaptDelta) {
+    CUDA_TRY(h, cudaMalloc(&h->d_adapt_hist, (size_t)c.n_chains * warmup_iter * sizeof(double)));
+    CUDA_TRY(h, cudaMemset(h->d_adapt_hist, 0, (size_t)c.n_chains * warmup_iter * sizeof(double)));
+  }
+  return WN_OK;
+}
+
 int wn_set_state(wn_handle* h, const double* q, int on_device) {
   if (!h || !q) return fail(h, WN_EINVAL, "wn_set_state: bad argument");
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
@@ -356,7 +404,8 @@ int wn_run_async(wn_handle* h, int64_t n_iter, double* d_draws, double* d_diag, 
     return fail(h, WN_ESTATE, "stock_watson needs data key y with T = d/3 entries");
   if (c.mode == WN_MODE_PACKAGE && !h->d_inv_mass) return fail(h, WN_ESTATE, "package mode needs data key inv_mass");
   LaunchPlan p;
-  if (!pick_plan(c, p)) return fail(h, WN_EUNSUPPORTED, "no CUDA kernel for this target/dimension");
+  const bool adapting = h->d_adapt_state != nullptr && h->iter_done < (uint32_t)h->warmup_iter;
+  if (!pick_plan(c, adapting, p)) return fail(h, WN_EUNSUPPORTED, "no CUDA kernel for this target/dimension");
   CUDA_TRY(h, cudaSetDevice(c.device));
   CUDA_TRY(h, cudaFuncSetAttribute(p.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
   int occ = 0;
@@ -383,6 +432,16 @@ int wn_run_async(wn_handle* h, int64_t n_iter, double* d_draws, double* d_diag, 
   tp.p0 = h->d_p0; tp.p1 = h->d_p1; tp.p2 = h->d_p2; tp.n0 = (int)h->n_p0; tp.n1 = (int)h->n_p1;
   tp.c0 = 1.0 / (h->tau * h->tau);
 
+  if (h->d_adapt_state && !adapting && !h->adapt_exported) {
+    // warm-up is over: freeze the adapted (H, delta) of every chain as its step size / tolerance
+    if (!h->d_H) CUDA_TRY(h, cudaMalloc(&h->d_H, (size_t)c.n_chains * sizeof(double)));
+    if (!h->d_delta) CUDA_TRY(h, cudaMalloc(&h->d_delta, (size_t)c.n_chains * sizeof(double)));
+    CUDA_TRY(h, cudaMemcpy2DAsync(h->d_H, sizeof(double), h->d_adapt_state, WN_ADAPT_STRIDE * sizeof(double),
+                                  sizeof(double), c.n_chains, cudaMemcpyDeviceToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpy2DAsync(h->d_delta, sizeof(double), h->d_adapt_state + 1, WN_ADAPT_STRIDE * sizeof(double),
+                                  sizeof(double), c.n_chains, cudaMemcpyDeviceToDevice, h->stream));
+    h->adapt_exported = true;
+  }
   CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
   if (!p.package) {
     RunParams P;
@@ -393,6 +452,10 @@ int wn_run_async(wn_handle* h, int64_t n_iter, double* d_draws, double* d_diag, 
     P.chain_offset = (uint32_t)c.chain_offset;
     P.H0 = c.H0; P.delta0 = c.delta; P.jitter = c.jitter; P.p0 = c.r2p_prob0;
     P.log_p0 = c.log_p0; P.log_1mp0 = c.log_1mp0;
+    P.warmup_iter = h->warmup_iter; P.adaptH = h->adaptH; P.adaptDelta = h->adaptDelta;
+    P.p2prob = 1.0 - h->adHtarget; P.adTarget = h->adTarget; P.adQuant = h->adQuant;
+    P.adapt_state = h->d_adapt_state; P.adapt_hist = h->d_adapt_hist;
+    // once adaptation has run, the adapted per-chain H / delta are the step sizes (WALNUTS.py:137,144)
     P.Hstep = h->d_H; P.delta = h->d_delta; P.state = h->d_state; P.draws = d_draws; P.diag = d_diag;
     P.nevalF = (unsigned long long*)d_nevalF; P.nevalB = (unsigned long long*)d_nevalB;
     P.totals = h->d_totals; P.scratch = h->d_scratch; P.nslot = nslot; P.queue = h->d_queue; P.tp = tp;

@@ -39,7 +39,13 @@ struct RunParams {
   int nslot;
   unsigned int* queue;
   TargetParams tp;
+  // warm-up adaptation (reference WALNUTS.py:136-147, 313, 701-712); ADAPT kernels only
+  int warmup_iter, adaptH, adaptDelta;
+  double p2prob, adTarget, adQuant;
+  double* adapt_state;   // [n_chains, WN_ADAPT_STRIDE]: H, delta, npush, q[5], n[5], hasNaN, nhist
+  double* adapt_hist;    // [n_chains, warmup_iter]: sorted history of orbitEnergyError / delta
 };
+#define WN_ADAPT_STRIDE 16
 
 enum { KIND_FIXED = 0, KIND_D = 1, KIND_R2P = 2 };
 enum { PH_FWD = 0, PH_REDO = 1, PH_BWD = 2 };
@@ -67,9 +73,12 @@ struct Ctl {
   double WoldSum, WnewSum, indexStat, indexStatOld, orbitLen, orbitLenSam;
   double sMinL, sMaxL, sHmax, sHmin;
   unsigned long long nF, nB, chainF, chainB;
+  // warm-up adaptation
+  int warm, p2npush, p2n[5], adNaN, adNhist;
+  double p2q[5], igr, maxd, Hprev;
 };
 
-template <template <int, int> class TargetTT, int G, int E2, int NT, int MINB = 1>
+template <template <int, int> class TargetTT, int G, int E2, int NT, int MINB = 1, bool ADAPT = false>
 __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_constant__ RunParams P) {
   constexpr int E = 2 * E2;
   constexpr int GPB = NT / G;  // groups per block
@@ -112,6 +121,10 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
   bool rsearch = false, rexact = false, rlazyok = false;
   double rh = 0, rHref = 0, rdelta = 0, rsign = 1.0;
   unsigned long long rEv = 0;
+  // ADAPT: per-step energies of the forward passes (igrConst, adaptiveIntegrators.py:101,399,424)
+  bool trackH = false;
+  double hist[4];
+  int nh = 0;
   unsigned long long totF = 0, totB = 0;
 
   auto useq = [&]() -> double {
@@ -148,6 +161,85 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
       umax = max(umax, max((unsigned)hq, (unsigned)hv));
     }
   };
+  // ADAPT: fold the batched per-step energy partials into max |diff(Hams)| (adaptiveIntegrators.py:101)
+  auto flush_hist = [&]() {
+    if constexpr (ADAPT) {
+      if (nh == 0) return;
+      double x[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) x[i] = (i < nh) ? hist[i] : 0.0;
+      Grp::template sum<4>(x, red, parity);
+      double md = C.maxd, hpv = C.Hprev;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (i < nh) {
+          const double dd = fabs(x[i] - hpv);
+          md = (dd > md || dd != dd) ? dd : md;     // np.max propagates NaN
+          hpv = x[i];
+        }
+      }
+      C.maxd = md;
+      C.Hprev = hpv;
+      nh = 0;
+    }
+  };
+  // ADAPT: P-squared quantile push, reference WALNUTSpy/P2quantile.py:41-89
+  auto p2_push = [&](double xi) {
+    if constexpr (ADAPT) {
+      const int np_ = C.p2npush + 1;
+      C.p2npush = np_;
+      if (np_ <= 5) {
+        C.p2q[np_ - 1] = xi;
+        if (np_ == 5) {                       // np.sort(x), :45-47 (NaN sorts last)
+          double a[5];
+#pragma unroll
+          for (int i = 0; i < 5; ++i) a[i] = C.p2q[i];
+          // insertion sort, NaN treated as +infinity-like (placed last), stable
+          for (int i = 1; i < 5; ++i) {
+            const double key = a[i];
+            int j = i - 1;
+            while (j >= 0 && ((a[j] > key) || (a[j] != a[j] && key == key))) { a[j + 1] = a[j]; --j; }
+            a[j + 1] = key;
+          }
+#pragma unroll
+          for (int i = 0; i < 5; ++i) C.p2q[i] = a[i];
+        }
+        return;
+      }
+      double q_[5];
+      int n_[5];
+#pragma unroll
+      for (int i = 0; i < 5; ++i) { q_[i] = C.p2q[i]; n_[i] = C.p2n[i]; }
+      int k;                                   // findInterval, :31-39,49-57
+      if (xi < q_[0]) { q_[0] = xi; k = 1; }
+      else if (xi > q_[4]) { q_[4] = xi; k = 4; }
+      else {
+        k = 0;                                 // fall-through (None): n[None:5] += 1 increments all
+        for (int i = 0; i < 4; ++i) if (xi < q_[i + 1]) { k = i + 1; break; }
+      }
+#pragma unroll
+      for (int i = 0; i < 5; ++i) if (i >= k) n_[i] += 1;        // :60
+      const double nn = (double)np_, pp = P.p2prob;
+      const double npp[5] = {1.0, 0.5 * (nn - 1.0) * pp + 1.0, (nn - 1.0) * pp + 1.0,
+                             (nn - 1.0) * (1.0 + pp) / 2.0 + 1.0, nn};
+      for (int i = 2; i <= 4; ++i) {           // :70-89
+        const int ni = n_[i - 1], nip = n_[i], nim = n_[i - 2];
+        double di = npp[i - 1] - (double)ni;
+        if ((di >= 1.0 && nip - ni > 1) || (di <= -1.0 && nim - ni < -1)) {
+          const int dI = (di > 0.0) ? 1 : -1;
+          const double qi = q_[i - 1];
+          const double qip = qi + ((double)dI / (double)(nip - nim)) *
+                                      ((double)(ni - nim + dI) * (q_[i] - qi) / (double)(nip - ni) +
+                                       (double)(nip - ni - dI) * (qi - q_[i - 2]) / (double)(ni - nim));
+          if (q_[i - 2] < qip && qip < q_[i]) q_[i - 1] = qip;
+          else q_[i - 1] = qi + (double)dI * (q_[i + dI - 1] - qi) / (double)(n_[i + dI - 1] - n_[i - 1]);
+          n_[i - 1] += dI;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 5; ++i) { C.p2q[i] = q_[i]; C.p2n[i] = n_[i]; }
+    }
+  };
   auto start_pass = [&](int cc) {
     steps_left = 1u << cc;
     hh = ldexp(rh, -cc);
@@ -156,8 +248,12 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
     smax = 0;
     umax = 0;
     if constexpr (Target::LAZY_ENERGY) {
-      lazy = rlazyok && !rexact && (cc >= 2);
+      lazy = rlazyok && !rexact && (cc >= 2) && !trackH;
       if (lazy) track_state();   // the pass starts from a bounded state
+    }
+    if constexpr (ADAPT) {
+      nh = 0;
+      if (trackH) { C.maxd = 0.0; C.Hprev = rHref; }
     }
   };
   // U-turn criterion, reference WALNUTS.py:95-97; (ql, vl) read from scratch, the other state is the
@@ -227,7 +323,14 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
     }
     // =============================== hot: leapfrog micro-steps ==================================
     if (st == ST_RUN) {
-      if (Target::LAZY_ENERGY && lazy && steps_left >= 3u) {
+      if (ADAPT && trackH) {   // warm-up: every step's energy is needed for igrConst
+        micro_step();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) hist[i] = (nh == i) ? hp : hist[i];
+        ++nh;
+        --steps_left;
+        if (nh == 4 || steps_left == 0u) flush_hist();
+      } else if (Target::LAZY_ENERGY && lazy && steps_left >= 3u) {
         micro_step_lazy();
         micro_step_lazy();
         track_state();
@@ -264,11 +367,18 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
             const int j = target.coord(e, t);
             q[e] = (j < P.d) ? P.state[(size_t)cidx * P.d + j] : 0.0;
           }
-          const double Hbig = P.Hstep ? P.Hstep[cidx] : P.H0;
-          C.Hbig = Hbig;
+          C.Hbig = P.Hstep ? P.Hstep[cidx] : P.H0;
           C.delta = P.delta ? P.delta[cidx] : P.delta0;
-          C.jlo = __dmul_rn(Hbig, __dadd_rn(1.0, -P.jitter));   // WALNUTS.py:298
-          C.jhi = __dmul_rn(Hbig, __dadd_rn(1.0, P.jitter));
+          if constexpr (ADAPT) {
+            const double* as = P.adapt_state + (size_t)cidx * WN_ADAPT_STRIDE;
+            C.Hbig = as[0];
+            C.delta = as[1];
+            C.p2npush = (int)as[2];
+#pragma unroll
+            for (int i = 0; i < 5; ++i) { C.p2q[i] = as[3 + i]; C.p2n[i] = (int)as[8 + i]; }
+            C.adNaN = (int)as[13];
+            C.adNhist = (int)as[14];
+          }
           C.it = 0;
           C.chainF = 0;
           C.chainB = 0;
@@ -279,6 +389,12 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
           RngKey key{P.seed_lo, P.seed_hi, C.chain, P.iter0 + (uint32_t)C.it};
           C.iter = key.iter;
           C.nseq = 0;
+          {
+            const double Hbig = C.Hbig;
+            C.jlo = __dmul_rn(Hbig, __dadd_rn(1.0, -P.jitter));   // WALNUTS.py:298
+            C.jhi = __dmul_rn(Hbig, __dadd_rn(1.0, P.jitter));
+          }
+          if constexpr (ADAPT) C.warm = (key.iter <= (uint32_t)P.warmup_iter) ? 1 : 0;   // :209
           uint32_t dirbits = 0;
           for (int k = 0; k < P.M; ++k) {
             const double u = rng_uniform(key, STREAM_DIR, (uint32_t)k);   // B = floor(U(0,2)), :216
@@ -402,6 +518,7 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
           rsearch = (P.kind != KIND_FIXED);
           rexact = false;
           rEv = 0;
+          if constexpr (ADAPT) trackH = C.warm && P.adaptH && (P.kind != KIND_FIXED);
           if constexpr (Target::LAZY_ENERGY) rlazyok = target.lazy_ok && (C.jhi <= 1024.0);
           if (P.kind != KIND_FIXED) save_ck();   // S = start state (integration convention)
           C.wIntact = 1;
@@ -481,6 +598,18 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
           if (phase != PH_BWD) {
             // forward simulation done: registers hold the out state O
             C.Hfwd = Hend;
+            if constexpr (ADAPT) {
+              if (C.warm && P.adaptH) {
+                if (P.kind == KIND_FIXED) {      // adaptiveIntegrators.py:59
+                  const double ad = fabs(C.Ham0 - Hend);
+                  C.igr = rh * pow((ad > 1.0e-10) ? ad : 1.0e-10, -1.0 / 3.0);
+                } else {                         // :101,399,424 (last forward pass)
+                  const double md = C.maxd;
+                  C.igr = (md > 0.0 || md != md) ? hh * pow(md, -1.0 / 3.0) : INFINITY;
+                }
+              }
+              trackH = false;
+            }
             if (P.kind == KIND_FIXED) {
               C.Ib = 0;
               C.lwt = 0.0;
@@ -499,6 +628,7 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
               C.phase = PH_BWD;
               C.c = P.minC;
               rc = P.minC; rlim = maxTry; rHref = Hend; rsign = -1.0; rsearch = true; rEv = 0;
+              if constexpr (ADAPT) trackH = false;
 #pragma unroll
               for (int e = 0; e < E; ++e) v[e] = -v[e];
               start_pass(P.minC);
@@ -536,6 +666,9 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
           break;
         }
         case ST_LEAF: {  // driver bookkeeping after a macro step, WALNUTS.py:302-368,398-570
+          if constexpr (ADAPT) {
+            if (C.warm && P.adaptH) p2_push(log(C.igr));    // :313,347,411,454,498,541
+          }
           const int level = C.level, side = C.side;
           const uint32_t nleaf = C.nleaf;
           const double h = C.h, Hfwd = C.Hfwd, lwt = C.lwt;
@@ -686,6 +819,58 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
             dg[18] = C.delta; dg[19] = C.stopCode; dg[20] = C.NdC; dg[21] = C.sMinC; dg[22] = C.sMaxC;
             dg[23] = C.indexStat;
           }
+          if constexpr (ADAPT) {
+            if (C.warm) {   // WALNUTS.py:701-712
+              double delta = C.delta;
+              if (P.adaptDelta) {
+                const double fac = (C.sHnan ? __longlong_as_double(0x7ff8000000000000ll) : C.sHmax - C.sHmin) / delta;  // :704
+                double* hrow = P.adapt_hist + (size_t)cidx * P.warmup_iter;
+                const int n0 = C.adNhist;             // finite / infinite entries stored so far (sorted)
+                int pos = n0;
+                if (fac != fac) {
+                  C.adNaN = 1;
+                } else {                              // upper-bound position in the sorted row
+                  int lo = 0, hi = n0;
+                  while (lo < hi) { const int mid = (lo + hi) >> 1; if (hrow[mid] <= fac) lo = mid + 1; else hi = mid; }
+                  pos = lo;
+                }
+                const int n1 = (fac != fac) ? n0 : n0 + 1;
+                // element i of the row after insertion, read from the row before insertion
+                auto at = [&](int i) -> double { return (fac != fac || i < pos) ? hrow[i] : (i == pos ? fac : hrow[i - 1]); };
+                const int iterN = (int)C.iter;
+                double newdelta = delta;
+                if (iterN > 10) {                     // :705-707, np.quantile(x[0:iterN], q) (method 'linear')
+                  double qv;
+                  if (C.adNaN) {
+                    qv = __longlong_as_double(0x7ff8000000000000ll);
+                  } else {
+                    const double nn = (double)n1, qq = P.adQuant;
+                    // numpy _compute_virtual_index(n, q, 1, 1): n*q + (1 + q*(1-1-1)) - 1
+                    const double virt = __dadd_rn(__dadd_rn(__dmul_rn(nn, qq), __dadd_rn(1.0, __dmul_rn(qq, -1.0))), -1.0);
+                    int prev = (int)floor(virt), next = prev + 1;
+                    if (virt >= nn - 1.0) { prev = n1 - 1; next = n1 - 1; }
+                    if (prev < 0) { prev = 0; }
+                    if (next < 0) { next = 0; }
+                    const double gam = virt - floor(virt);
+                    const double a = at(prev), b = at(next);
+                    const double dba = b - a;                                   // numpy _lerp
+                    qv = (gam >= 0.5) ? (b - dba * (1.0 - gam)) : (a + dba * gam);
+                  }
+                  newdelta = P.adTarget / qv;
+                }
+                if constexpr (G > 32) __syncthreads(); else if constexpr (G > 1) __syncwarp(Grp::mask());
+                if (t == 0 && fac == fac) {           // shift the tail and insert
+                  for (int i = n0; i > pos; --i) hrow[i] = hrow[i - 1];
+                  hrow[pos] = fac;
+                }
+                if constexpr (G > 32) __syncthreads(); else if constexpr (G > 1) __syncwarp(Grp::mask());
+                C.adNhist = n1;
+                delta = newdelta;
+                C.delta = delta;
+              }
+              if (P.adaptH && C.p2npush > 10) C.Hbig = pow(delta, 1.0 / 3.0) * exp(C.p2q[2]);   // :711-712
+            }
+          }
           const unsigned long long cf = C.chainF + nF, cbk = C.chainB + nB;
           C.chainF = cf;
           C.chainB = cbk;
@@ -702,6 +887,13 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
           if (t == 0) {
             if (P.nevalF) P.nevalF[cidx] = cf;
             if (P.nevalB) P.nevalB[cidx] = cbk;
+            if constexpr (ADAPT) {
+              double* as = P.adapt_state + (size_t)cidx * WN_ADAPT_STRIDE;
+              as[0] = C.Hbig; as[1] = C.delta; as[2] = (double)C.p2npush;
+#pragma unroll
+              for (int i = 0; i < 5; ++i) { as[3 + i] = C.p2q[i]; as[8 + i] = (double)C.p2n[i]; }
+              as[13] = (double)C.adNaN; as[14] = (double)C.adNhist;
+            }
           }
           totF += cf;
           totB += cbk;

@@ -94,6 +94,13 @@ class ChainBatch:
         p, dev = _ptr(arr)
         self._check(self._lib.wn_set_data(self._h, key.encode(), p, n, dev), f"wn_set_data({key})")
 
+    def set_adapt(self, warmup_iter, adaptH=True, adaptHtarget=0.8, adaptDelta=True, adaptDeltaTarget=0.6,
+                  adaptDeltaQuantile=0.9):
+        """Warm-up adaptation of H and delta per chain (WALNUTS.py:136-147, 701-712)."""
+        rc = self._lib.wn_set_adapt(self._h, int(warmup_iter), int(bool(adaptH)), float(adaptHtarget),
+                                    int(bool(adaptDelta)), float(adaptDeltaTarget), float(adaptDeltaQuantile))
+        self._check(rc, "wn_set_adapt")
+
     def set_state(self, q):
         if not _is_torch(q):
             q = np.ascontiguousarray(np.broadcast_to(np.asarray(q, dtype=np.float64), (self.n_chains, self.d)))
