@@ -133,6 +133,23 @@ def cpu_baseline(iters=1, cores=None):
             "per_core": evals / busy / cores}
 
 
+def cpu_baseline_c(iters=1, cores=None, chains_per_core=4):
+    """The same workload on the C restatement (oracle/c/walnuts_oracle.c, -O3, pthreads): the strong CPU
+    baseline standing in for the absent walnuts_cpp."""
+    from oracle import c_oracle
+    cores = cores or os.cpu_count() or 1
+    sigma = sigma_vec()
+    n = cores * chains_per_core
+    q = np.ascontiguousarray(init_positions(n, 0, sigma))
+    t0 = time.perf_counter()
+    evals = c_oracle.run_many("diag_gauss", "R2P", q, CFG["H0"], CFG["delta"], CFG["M"], iters, SEED, cores,
+                              minC=CFG["minC"], maxC=CFG["maxC"], inv_var=1.0 / sigma ** 2, jitter=CFG["jitter"])
+    dt = time.perf_counter() - t0
+    return {"value": evals / dt, "unit": "grad_evals/s", "cores": cores, "kind": "port-c",
+            "sample": f"{n} chains x {iters} transition(s) on {cores} pthreads (C restatement, gcc -O3 -mavx2; "
+                      f"{evals} evals in {dt:.1f}s)", "per_core": evals / dt / cores}
+
+
 # --------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -162,7 +179,11 @@ def main():
             cb = cpu_baseline(args.cpu_iters)
             vals.append(cb["value"])
         cb["value"] = float(np.mean(vals))
-        line = {"impl": "reference", "metric": "grad_evals_per_sec", "value": cb["value"], "unit": "grad_evals/s",
+        try:
+            extra_c = cpu_baseline_c(args.cpu_iters)
+        except Exception as e:
+            extra_c = {"unavailable": str(e)[:200]}
+        line = {"impl": "reference", "cpu_baseline_c": extra_c, "metric": "grad_evals_per_sec", "value": cb["value"], "unit": "grad_evals/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": None,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "config": config, "cpu_baseline": cb,
@@ -294,6 +315,10 @@ def main():
     }
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(args.cpu_iters)
+        try:
+            line["cpu_baseline_c"] = cpu_baseline_c(args.cpu_iters)
+        except Exception as e:                                   # the C checker is optional for the bench
+            line["cpu_baseline_c"] = {"unavailable": str(e)[:200]}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

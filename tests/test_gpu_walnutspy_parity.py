@@ -251,3 +251,51 @@ def test_logreg(cuda_lib, integrator, N, P):
     if integrator == "fixed":
         H0 *= 0.5
     check("logreg", q0, integrator, H0=H0, delta=0.3, M=6, n_iter=8, data=data, chains=[0, 4, 8], float_rtol=1e-8)
+
+
+@pytest.mark.parametrize("integrator", ["fixed", "D", "R2P"])
+def test_forced_reject_non_finite_energy(cuda_lib, integrator):
+    """Numerical-failure path: a wildly unstable step size drives the energy to inf/NaN, the reference
+    force-rejects (stop code 999, WALNUTS.py:316-319,414-417,457-459 and quirks A14 ii/iii).  Also covers
+    the lazy-energy fallback (state magnitudes beyond the 2^300 bound force the exact per-step path)."""
+    d = 6
+    sigma = np.array([1e-3, 1e-2, 1.0, 1.0, 10.0, 100.0])
+    data = {"inv_var": 1.0 / sigma ** 2}
+    q0 = q0_for(6, d) * sigma
+    q0[3] *= 1e150                      # one chain starts where q^2 overflows
+    dg = check("diag_gauss", q0, integrator, H0=40.0, delta=0.3, M=6, n_iter=12, data=data, maxC=4,
+               float_rtol=1e-6)
+    assert (dg[..., 19] == 999).any(), np.unique(dg[..., 19])
+
+
+def test_single_chain_single_iteration_edge_sizes(cuda_lib):
+    """Smallest shapes: one chain, one transition, d = 1 and d = 2, dg < d."""
+    from walnuts_b200 import ChainBatch
+    for d in (1, 2, 5):
+        q0 = q0_for(1, d, seed=d)
+        check("std_normal", q0, "R2P", H0=0.7, delta=0.3, M=3, n_iter=1)
+        with ChainBatch("std_normal", d, 1, integrator="D", H0=0.7, delta=0.3, M=3, seed=2, dg=1) as cb:
+            cb.set_state(q0)
+            out = cb.run(2, draws=True)
+            assert out["draws"].shape == (2, 1, 1)
+            assert np.array_equal(out["draws"][-1, 0], cb.get_state()[0, :1])
+
+
+@pytest.mark.parametrize("integrator", ["fixed", "D", "R2P"])
+def test_c2_100_transitions_vs_c_oracle(cuda_lib, integrator):
+    """north_star parity statement at the BASELINE config-2 shape: d = 1000, sigma = logspace(-2, 2),
+    H0 = 0.5 / 0.008, delta = 0.3, M = 10 -- the first 100 free-running transitions agree to 1e-10 with the
+    CPU restatement fed the same Philox streams (C oracle, itself pinned to the reference's goldens)."""
+    from oracle import c_oracle
+    d, n_iter = 1000, 100
+    sigma = np.logspace(-2, 2, d)
+    inv_var = 1.0 / sigma ** 2
+    q0 = q0_for(40, d, seed=9) * sigma
+    H0 = 0.008 if integrator == "fixed" else 0.5
+    out, _ = run_cuda("diag_gauss", q0, integrator, H0, 0.3, 10, n_iter, 4242, data={"inv_var": inv_var})
+    for c in (0, 39):
+        dr, dg, ne = c_oracle.run_chain("diag_gauss", integrator, q0[c], H0, 0.3, 10, n_iter, 4242, c, inv_var=inv_var)
+        ok, err = close(out["draws"][:, c, :], dr)
+        assert ok, f"chain {c}: max rel err {err:.3e}"
+        assert np.array_equal(out["diag"][:, c][:, EXACT_COLS], dg[:, EXACT_COLS])
+        assert int(out["nevalF"][c] + out["nevalB"][c]) == ne
