@@ -1,5 +1,6 @@
 // C-ABI of the B200-native WALNUTS/NUTS sampler (include/walnuts_cuda.h).
 // Host side: handle management, kernel dispatch by (target, dimension), launch + timing.
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -35,6 +36,7 @@ struct wn_handle {
   double adHtarget = 0.8, adTarget = 0.6, adQuant = 0.9;
   int64_t n_p0 = 0, n_p1 = 0;
   double tau = 1.0;
+  double inv_var_max = 1.0;
   uint32_t iter_done = 0;
   float last_ms = 0.f;
   int64_t last_launches = 0;
@@ -295,7 +297,13 @@ int wn_set_data(wn_handle* h, const char* key, const double* ptr, int64_t n, int
   if (!strcmp(key, "inv_var")) {
     if (n != c.d) return fail(h, WN_EINVAL, "inv_var must have d entries");
     h->n_p0 = n;
-    return upload(h, &h->d_p0, ptr, n, on_device);
+    int rc = upload(h, &h->d_p0, ptr, n, on_device);
+    if (rc) return rc;
+    std::vector<double> tmp((size_t)n);
+    CUDA_TRY(h, cudaMemcpy(tmp.data(), h->d_p0, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
+    h->inv_var_max = 0.0;
+    for (double x : tmp) h->inv_var_max = (fabs(x) > h->inv_var_max || x != x) ? fabs(x) : h->inv_var_max;
+    return WN_OK;
   }
   if (!strcmp(key, "inv_mass")) {
     if (n != c.d) return fail(h, WN_EINVAL, "size mismatch between theta and inv_mass");
@@ -430,7 +438,7 @@ int wn_run_async(wn_handle* h, int64_t n_iter, double* d_draws, double* d_diag, 
 
   TargetParams tp;
   tp.p0 = h->d_p0; tp.p1 = h->d_p1; tp.p2 = h->d_p2; tp.n0 = (int)h->n_p0; tp.n1 = (int)h->n_p1;
-  tp.c0 = 1.0 / (h->tau * h->tau);
+  tp.c0 = (c.target == WN_TARGET_DIAG_GAUSS) ? h->inv_var_max : 1.0 / (h->tau * h->tau);
 
   if (h->d_adapt_state && !adapting && !h->adapt_exported) {
     // warm-up is over: freeze the adapted (H, delta) of every chain as its step size / tolerance

@@ -40,9 +40,12 @@ struct DiagGaussT {
   __host__ __device__ static constexpr int smem_doubles(int) { return 0; }
   __device__ __forceinline__ int coord(int e, int t) const { return coord_of<G>(e, t); }
   double s[UNIT ? 1 : E];
+  double smax;     // max inv_var over ALL coordinates (host-computed, TargetParams::c0)
   bool lazy_ok;
   __device__ __forceinline__ void init(const TargetParams& tp, int d, int t, double*) {
     lazy_ok = true;
+    smax = UNIT ? 1.0 : tp.c0;
+    lazy_ok = (smax <= 0x1p60);
     if constexpr (!UNIT) {
 #pragma unroll
       for (int e = 0; e < E; ++e) {
@@ -62,6 +65,12 @@ struct DiagGaussT {
       else acc0 = fma(q[e], g[e], acc0);
     }
     return 0.5 * (acc0 + acc1);
+  }
+  // upper bound of max(|q'|,|v'|) / max(|q|,|v|) over one leapfrog step of size hh on this target:
+  // v1 = v - a s q, q' = q + hh v1, v' = v1 - a s q'  with a = hh/2, s <= smax
+  __device__ __forceinline__ double step_growth(double hh) const {
+    const double A = 0.5 * hh * smax;
+    return fmax(1.0 + hh + hh * A, 1.0 + 2.0 * A + hh * A + hh * A * A);
   }
   __device__ __forceinline__ void grad_only(const double (&q)[E], double (&g)[E]) const {
 #pragma unroll

@@ -116,6 +116,7 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
   int smax = 0;            // lazy-energy passes: signed / unsigned max of the high words of q, v
   unsigned umax = 0;
   bool lazy = false;       // current pass skips intermediate energies
+  int since = 0, lazyK = 2; // skipped steps since the last magnitude check / allowed between checks
   // register copy of the step-size search state: a failed attempt goes straight to the next one
   int rc = 0, rlim = 0;
   bool rsearch = false, rexact = false, rlazyok = false;
@@ -249,7 +250,16 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
     umax = 0;
     if constexpr (Target::LAZY_ENERGY) {
       lazy = rlazyok && !rexact && (cc >= 2) && !trackH;
-      if (lazy) track_state();   // the pass starts from a bounded state
+      if (lazy) {
+        track_state();   // the pass starts from a bounded state
+        since = 0;
+        // One leapfrog step amplifies max(|q|,|v|) by at most Gamma (target-specific bound); checked
+        // states are below 2^300, so up to floor(180 / log2 Gamma) steps may pass between checks while
+        // every skipped energy stays finite (< 2^480 magnitudes).
+        const double lg = log2(target.step_growth(hh));
+        lazyK = (lg * 64.0 <= 180.0) ? 64 : max(2, (int)(180.0 / lg));
+        lazyK &= ~1;
+      }
     }
     if constexpr (ADAPT) {
       nh = 0;
@@ -298,8 +308,8 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
   // are bounded: the high words are max-reduced as signed ints (largest positive value) and as
   // unsigned ints (largest-magnitude negative value) -- two 3-input integer max per coordinate, off the
   // FP64 pipe -- at the pass start and after every second skipped step.  With inv_var <= 2^60 and a
-  // micro step <= 2^10 one leapfrog step amplifies |q|, |v| by at most 2^142, so "checked states below
-  // 2^300" implies every state in between is below 2^442 and every skipped energy is finite.
+  // micro step <= 2^10 one leapfrog step amplifies |q|, |v| by at most 2^142 in the worst case; start_pass() derives the actual per-step bound Gamma and the number of steps
+  // that may pass between two checks.
   auto micro_step_lazy = [&]() {
     if constexpr (Target::LAZY_ENERGY) {
 #pragma unroll
@@ -331,10 +341,22 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
         --steps_left;
         if (nh == 4 || steps_left == 0u) flush_hist();
       } else if (Target::LAZY_ENERGY && lazy && steps_left >= 3u) {
-        micro_step_lazy();
-        micro_step_lazy();
-        track_state();
-        steps_left -= 2u;
+        if constexpr (G >= 32 && !Target::BLOCK_LOCKSTEP) {
+          // the whole warp follows one chain: stay in a tight loop for the skipped-energy steps
+          do {
+            micro_step_lazy();
+            micro_step_lazy();
+            steps_left -= 2u;
+            since += 2;
+            if (since >= lazyK) { track_state(); since = 0; }
+          } while (steps_left >= 3u);
+        } else {
+          micro_step_lazy();
+          micro_step_lazy();
+          steps_left -= 2u;
+          since += 2;
+          if (since >= lazyK) { track_state(); since = 0; }
+        }
       } else if (Target::LAZY_ENERGY && lazy && steps_left == 2u) {
         micro_step_lazy();
         micro_step();
