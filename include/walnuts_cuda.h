@@ -121,6 +121,12 @@ int wn_get_state(wn_handle* h, double* q, int on_device);
 int wn_run(wn_handle* h, int64_t n_iter, double* draws, double* diag, uint64_t* nevalF,
            uint64_t* nevalB, int on_device);
 
+/* wn_run plus the per-iteration orbit statistics of WALNUTS(recordOrbitStats=True) (WALNUTS.py:182-184,
+ * 274-276, 331-333, ...): orbit_min / orbit_max [n_iter, n_chains, dg] = element-wise min / max of the leading
+ * dg coordinates over every state visited by the orbit of that iteration (both NULL to skip). */
+int wn_run_stats(wn_handle* h, int64_t n_iter, double* draws, double* diag, uint64_t* nevalF,
+                 uint64_t* nevalB, double* orbit_min, double* orbit_max, int on_device);
+
 /* Same, asynchronous on the handle's stream with device buffers only; pair with wn_sync(). */
 int wn_run_async(wn_handle* h, int64_t n_iter, double* d_draws, double* d_diag,
                  uint64_t* d_nevalF, uint64_t* d_nevalB);

@@ -127,7 +127,7 @@ def macro_step(kind, q, v, g, Ham0, h, xi, lpFun, delta, aux, rng):
     return dict(q=qO, v=xi * vO, grad=gO, H=HO, nF=nF, nB=nB, If=If, Ib=Ib, c=cSim, lwt=lwt, igrConst=igr)
 
 
-def transition(lpFun, qc, rng, kind, H, delta, M, aux, jitter=0.2, igr_sink=None):
+def transition(lpFun, qc, rng, kind, H, delta, M, aux, jitter=0.2, igr_sink=None, orbit=None):
     """One WALNUTSpy iteration (WALNUTS.py:196-693).  Returns (q_next, diag[24])."""
     d = qc.size
     B = np.floor(rng.dir_uniform02(M)).astype(int)                      # :216
@@ -156,6 +156,9 @@ def transition(lpFun, qc, rng, kind, H, delta, M, aux, jitter=0.2, igr_sink=None
               nne=0, nz=0, Hmax=H0, Hmin=H0, Hnan=False)
     lo = H * (1 - jitter)
     hi = H * (1 + jitter)
+    if orbit is not None:               # recordOrbitStats, WALNUTS.py:274-276
+        orbit["min"] = np.array(qc, dtype=np.float64)
+        orbit["max"] = np.array(qc, dtype=np.float64)
 
     def record(o):
         st["n"] += 1
@@ -213,6 +216,9 @@ def transition(lpFun, qc, rng, kind, H, delta, M, aux, jitter=0.2, igr_sink=None
             elif not (side == 1 and n % 2 == 0):
                 lwtSum[side] += o["lwt"]    # quirk A14(i): :420 has no counterpart after :443-459
             Wnew = float(np.exp(-o["H"] + H0 + lwtSum[side]))           # :322,355,422,462,510,552
+            if orbit is not None:       # :331-333,364-366,434-436,474-476,521-523,564-566
+                orbit["min"] = np.minimum(orbit["min"], o["q"])
+                orbit["max"] = np.maximum(orbit["max"], o["q"])
             if i == 0:
                 WnewSum = Wnew
                 qProp, L_, indexStat = o["q"], xi, xi * timeLen[side]   # :326-328,359-361
@@ -379,7 +385,7 @@ class NumpyGlobalRNG:
 def WALNUTS(lpFun, q0, generated=lambda q: q, integrator=FIXED, H0=0.2, stepSizeRandScale=0.2,
             delta0=0.05, numIter=2000, M=10, igrAux=None, rng=None, seed=0, chain=0,
             first_iteration=1, warmupIter=0, adaptH=False, adaptHtarget=0.8, adaptDelta=False,
-            adaptDeltaTarget=0.6, adaptDeltaQuantile=0.9):
+            adaptDeltaTarget=0.6, adaptDeltaQuantile=0.9, recordOrbitStats=False):
     """WALNUTSpy chain incl. the warm-up adaptation of H and delta (WALNUTS.py:136-147, 313, 701-712).
     Returns (samples (dg, numIter+1), diagnostics (numIter, 24)) like WALNUTS.py:724-727."""
     from . import philox
@@ -394,6 +400,8 @@ def WALNUTS(lpFun, q0, generated=lambda q: q, integrator=FIXED, H0=0.2, stepSize
     samples[:, 0] = g0
     diagnostics = np.zeros((numIter, 24))
     H, delta = H0, delta0
+    orbitMin = np.zeros((qc.size, numIter))
+    orbitMax = np.zeros((qc.size, numIter))
     p2 = P2Quantile(1.0 - adaptHtarget) if adaptH else None                    # :139-141
     facs = np.zeros(warmupIter) if adaptDelta else None                         # :145-147
     for it in range(1, numIter + 1):
@@ -405,8 +413,11 @@ def WALNUTS(lpFun, q0, generated=lambda q: q, integrator=FIXED, H0=0.2, stepSize
             with np.errstate(all="ignore"):
                 sink = lambda c: p2.push(np.log(c))                             # :313
         with np.errstate(all="ignore"):
+            orb = {} if recordOrbitStats else None
             qc, diagnostics[it - 1] = transition(lpFun, qc, rng, integrator, H, delta, M, aux,
-                                                 jitter=stepSizeRandScale, igr_sink=sink)
+                                                 jitter=stepSizeRandScale, igr_sink=sink, orbit=orb)
+            if recordOrbitStats:
+                orbitMin[:, it - 1], orbitMax[:, it - 1] = orb["min"], orb["max"]
             samples[:, it] = generated(qc)
             if warmup:                                                          # :701-712
                 if adaptDelta:
@@ -415,4 +426,6 @@ def WALNUTS(lpFun, q0, generated=lambda q: q, integrator=FIXED, H0=0.2, stepSize
                     delta = adaptDeltaTarget / np.quantile(facs[0:it], adaptDeltaQuantile)
                 if adaptH and p2.npush > 10:
                     H = (delta ** (1.0 / 3.0)) * np.exp(p2.quantile())
+    if recordOrbitStats:
+        return samples, diagnostics, orbitMin, orbitMax
     return samples, diagnostics

@@ -64,3 +64,22 @@ def test_funnel_adaptation_prefix(cuda_lib):
     assert horizon >= 20, err[:25]
     ok, e2 = close(dg[:, :15, [15, 18]], do[:, :15, [15, 18]], rtol=1e-7)
     assert ok, e2
+
+
+@pytest.mark.parametrize("integrator", ["fixed", "R2P"])
+def test_record_orbit_stats(cuda_lib, integrator):
+    """WALNUTS(recordOrbitStats=True) (WALNUTS.py:182-184,274-276,331-333,...): per-iteration element-wise
+    min / max over every state of the orbit, returned as (dg, numIter) arrays after samples, diagnostics."""
+    import walnuts_b200 as wb
+    ig = {"fixed": wb.fixedLeapFrog, "R2P": wb.adaptLeapFrogR2P}[integrator]
+    q0 = 0.5 * np.random.default_rng(8).standard_normal((3, 5))
+    s, d, lo, hi = wb.WALNUTS(wb.targets.stdGauss, q0, integrator=ig, numIter=60, warmupIter=20, M=7, seed=5,
+                              recordOrbitStats=True)
+    assert lo.shape == (3, 5, 60) and hi.shape == (3, 5, 60)
+    for c in range(3):
+        so, do, lo_o, hi_o = wo.WALNUTS(ot.std_normal, q0[c], integrator=KIND[integrator], numIter=60, warmupIter=20,
+                                        M=7, seed=5, chain=c, adaptH=True, adaptDelta=True, recordOrbitStats=True)
+        for a, b in ((s[c], so), (lo[c], lo_o), (hi[c], hi_o)):
+            ok, err = close(a, b)
+            assert ok, err
+    assert (lo <= s[:, :, 1:]).all() and (s[:, :, 1:] <= hi).all()

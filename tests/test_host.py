@@ -43,7 +43,7 @@ def test_python_callables_are_rejected_loudly(cuda_lib):
     with pytest.raises(TypeError):
         wb.targets.stdGauss(np.zeros(3))
     with pytest.raises(NotImplementedError):
-        wb.WALNUTS(wb.targets.stdGauss, np.zeros(3), numIter=1, warmupIter=0, recordOrbitStats=True)
+        wb.WALNUTS(wb.targets.stdGauss, np.zeros(3), generated=lambda q: q[:1], numIter=1, warmupIter=0, recordOrbitStats=True)
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):

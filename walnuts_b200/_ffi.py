@@ -13,7 +13,7 @@ ERRORS = {-1: "WN_EINVAL", -2: "WN_ECUDA", -3: "WN_ENOMEM", -4: "WN_EUNSUPPORTED
 
 # every symbol include/walnuts_cuda.h declares
 SYMBOLS = ["wn_abi_version", "wn_target_id", "wn_create", "wn_destroy", "wn_set_data", "wn_set_adapt", "wn_set_state",
-           "wn_get_state", "wn_run", "wn_run_async", "wn_sync", "wn_last_kernel_ms", "wn_last_launches",
+           "wn_get_state", "wn_run", "wn_run_stats", "wn_run_async", "wn_sync", "wn_last_kernel_ms", "wn_last_launches",
            "wn_last_grad_evals", "wn_moments", "wn_stream", "wn_last_error", "wn_fp64_peak"]
 
 
@@ -59,6 +59,7 @@ def load():
     lib.wn_set_state.argtypes = [vp, dp, C.c_int]
     lib.wn_get_state.argtypes = [vp, dp, C.c_int]
     lib.wn_run.argtypes = [vp, C.c_int64, dp, dp, u64p, u64p, C.c_int]
+    lib.wn_run_stats.argtypes = [vp, C.c_int64, dp, dp, u64p, u64p, dp, dp, C.c_int]
     lib.wn_run_async.argtypes = [vp, C.c_int64, dp, dp, u64p, u64p]
     lib.wn_sync.argtypes = [vp]
     lib.wn_last_kernel_ms.argtypes = [vp, P(C.c_float)]

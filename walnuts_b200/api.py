@@ -34,8 +34,9 @@ def WALNUTS(lpFun, q0, generated=None, integrator=_ig.fixedLeapFrog, H0=0.2, ste
         raise ValueError("bad adaptHtarget")          # sys.exit in the reference, WALNUTS.py:140
     if adaptDelta and adaptDeltaTarget < 0.0:
         raise ValueError("bad adaptDeltaTarget")      # WALNUTS.py:146
-    if recordOrbitStats:
-        raise NotImplementedError("recordOrbitStats (WALNUTS.py:182-184) is not implemented (SURVEY.md row N2)")
+    if recordOrbitStats and generated is not None:
+        raise NotImplementedError("recordOrbitStats with a custom `generated` is not available on the GPU: the "
+                                  "orbit statistics are kept for the coordinates themselves (generated=None)")
     if not isinstance(integrator, _ig._Integrator):
         raise TypeError("integrator must be one of walnuts_b200.fixedLeapFrog / adaptLeapFrogD / adaptLeapFrogR2P")
     aux = igrAux or _ig.integratorAuxPar()
@@ -57,10 +58,11 @@ def WALNUTS(lpFun, q0, generated=None, integrator=_ig.fixedLeapFrog, H0=0.2, ste
         nw = min(warmupIter, numIter) if (adaptH or adaptDelta) else 0
         parts = []
         if nw > 0:
-            parts.append(cb.run(nw, draws=True, diag=True))          # adapting iterations
+            parts.append(cb.run(nw, draws=True, diag=True, orbit_stats=recordOrbitStats))    # adapting iterations
         if numIter - nw > 0:
-            parts.append(cb.run(numIter - nw, draws=True, diag=True))
-        out = {k: np.concatenate([p_[k] for p_ in parts]) for k in ("draws", "diag")}
+            parts.append(cb.run(numIter - nw, draws=True, diag=True, orbit_stats=recordOrbitStats))
+        keys = ("draws", "diag") + (("orbit_min", "orbit_max") if recordOrbitStats else ())
+        out = {k: np.concatenate([p_[k] for p_ in parts]) for k in keys}
     draws = out["draws"]                                    # (numIter, n_chains, d)
     gen = generated if generated is not None else (lambda x: x)
     g0 = np.asarray(gen(q[0]))
@@ -74,6 +76,12 @@ def WALNUTS(lpFun, q0, generated=None, integrator=_ig.fixedLeapFrog, H0=0.2, ste
             for i in range(numIter):
                 samples[c, :, i + 1] = gen(draws[i, c])
     diagnostics = np.ascontiguousarray(np.transpose(out["diag"], (1, 0, 2)))   # (n_chains, numIter, 24)
+    if recordOrbitStats:                                    # (dg, numIter) per chain, WALNUTS.py:183-184,724-725
+        omin = np.ascontiguousarray(np.transpose(out["orbit_min"], (1, 2, 0)))
+        omax = np.ascontiguousarray(np.transpose(out["orbit_max"], (1, 2, 0)))
+        if single:
+            return samples[0], diagnostics[0], omin[0], omax[0]
+        return samples, diagnostics, omin, omax
     if single:
         return samples[0], diagnostics[0]
     return samples, diagnostics

@@ -399,9 +399,19 @@ int wn_get_state(wn_handle* h, double* q, int on_device) {
   return WN_OK;
 }
 
+static int run_async_impl(wn_handle* h, int64_t n_iter, double* d_draws, double* d_diag, uint64_t* d_nevalF,
+                          uint64_t* d_nevalB, double* d_omin, double* d_omax);
+
 int wn_run_async(wn_handle* h, int64_t n_iter, double* d_draws, double* d_diag, uint64_t* d_nevalF,
                  uint64_t* d_nevalB) {
+  return run_async_impl(h, n_iter, d_draws, d_diag, d_nevalF, d_nevalB, nullptr, nullptr);
+}
+
+static int run_async_impl(wn_handle* h, int64_t n_iter, double* d_draws, double* d_diag, uint64_t* d_nevalF,
+                          uint64_t* d_nevalB, double* d_omin, double* d_omax) {
   if (!h) return WN_EINVAL;
+  if ((d_omin == nullptr) != (d_omax == nullptr)) return fail(h, WN_EINVAL, "orbit_min and orbit_max go together");
+  if (d_omin && h->cfg.mode != WN_MODE_WALNUTSPY) return fail(h, WN_EINVAL, "orbit statistics exist in WALNUTSPY mode only");
   if (n_iter <= 0 || n_iter > 0x7fffffff) return fail(h, WN_EINVAL, "n_iter must be positive");
   if (!h->have_state) return fail(h, WN_ESTATE, "wn_run before wn_set_state");
   const wn_config& c = h->cfg;
@@ -465,6 +475,7 @@ int wn_run_async(wn_handle* h, int64_t n_iter, double* d_draws, double* d_diag, 
     P.adapt_state = h->d_adapt_state; P.adapt_hist = h->d_adapt_hist;
     // once adaptation has run, the adapted per-chain H / delta are the step sizes (WALNUTS.py:137,144)
     P.Hstep = h->d_H; P.delta = h->d_delta; P.state = h->d_state; P.draws = d_draws; P.diag = d_diag;
+    P.orbit_min = d_omin; P.orbit_max = d_omax;
     P.nevalF = (unsigned long long*)d_nevalF; P.nevalB = (unsigned long long*)d_nevalB;
     P.totals = h->d_totals; P.scratch = h->d_scratch; P.nslot = nslot; P.queue = h->d_queue; P.tp = tp;
     void* args[] = {&P};
@@ -500,9 +511,15 @@ int wn_sync(wn_handle* h) {
 
 int wn_run(wn_handle* h, int64_t n_iter, double* draws, double* diag, uint64_t* nevalF, uint64_t* nevalB,
            int on_device) {
+  return wn_run_stats(h, n_iter, draws, diag, nevalF, nevalB, nullptr, nullptr, on_device);
+}
+
+int wn_run_stats(wn_handle* h, int64_t n_iter, double* draws, double* diag, uint64_t* nevalF, uint64_t* nevalB,
+                 double* orbit_min, double* orbit_max, int on_device) {
   if (!h) return WN_EINVAL;
+  if ((orbit_min == nullptr) != (orbit_max == nullptr)) return fail(h, WN_EINVAL, "orbit_min and orbit_max go together");
   if (on_device) {
-    int rc = wn_run_async(h, n_iter, draws, diag, nevalF, nevalB);
+    int rc = run_async_impl(h, n_iter, draws, diag, nevalF, nevalB, orbit_min, orbit_max);
     if (rc) return rc;
     return wn_sync(h);
   }
@@ -511,10 +528,11 @@ int wn_run(wn_handle* h, int64_t n_iter, double* draws, double* diag, uint64_t* 
   CUDA_TRY(h, cudaSetDevice(c.device));
   const size_t nd = draws ? (size_t)n_iter * c.n_chains * c.dg : 0;
   const size_t ng = diag ? (size_t)n_iter * c.n_chains * WN_DIAG_COLS : 0;
-  double *dd = nullptr, *dgp = nullptr;
+  double *dd = nullptr, *dgp = nullptr, *dlo = nullptr, *dhi = nullptr;
   uint64_t *df = nullptr, *db = nullptr;
   int rc = WN_OK;
-  auto cleanup = [&]() { cudaFree(dd); cudaFree(dgp); cudaFree(df); cudaFree(db); };
+  const size_t no = orbit_min ? (size_t)n_iter * c.n_chains * c.dg : 0;
+  auto cleanup = [&]() { cudaFree(dd); cudaFree(dgp); cudaFree(df); cudaFree(db); cudaFree(dlo); cudaFree(dhi); };
 #define TRY_OR_CLEAN(expr)                                                              \
   do {                                                                                  \
     cudaError_t _e = (expr);                                                            \
@@ -524,14 +542,19 @@ int wn_run(wn_handle* h, int64_t n_iter, double* draws, double* diag, uint64_t* 
     }                                                                                   \
   } while (0)
   if (nd) TRY_OR_CLEAN(cudaMalloc(&dd, nd * sizeof(double)));
+  if (no) { TRY_OR_CLEAN(cudaMalloc(&dlo, no * sizeof(double))); TRY_OR_CLEAN(cudaMalloc(&dhi, no * sizeof(double))); }
   if (ng) TRY_OR_CLEAN(cudaMalloc(&dgp, ng * sizeof(double)));
   if (nevalF) TRY_OR_CLEAN(cudaMalloc(&df, (size_t)c.n_chains * sizeof(uint64_t)));
   if (nevalB) TRY_OR_CLEAN(cudaMalloc(&db, (size_t)c.n_chains * sizeof(uint64_t)));
   if (db) TRY_OR_CLEAN(cudaMemsetAsync(db, 0, (size_t)c.n_chains * sizeof(uint64_t), h->stream));
-  rc = wn_run_async(h, n_iter, dd, dgp, df, db);
+  rc = run_async_impl(h, n_iter, dd, dgp, df, db, dlo, dhi);
   if (rc == WN_OK) rc = wn_sync(h);
   if (rc != WN_OK) { cleanup(); return rc; }
   if (nd) TRY_OR_CLEAN(cudaMemcpy(draws, dd, nd * sizeof(double), cudaMemcpyDeviceToHost));
+  if (no) {
+    TRY_OR_CLEAN(cudaMemcpy(orbit_min, dlo, no * sizeof(double), cudaMemcpyDeviceToHost));
+    TRY_OR_CLEAN(cudaMemcpy(orbit_max, dhi, no * sizeof(double), cudaMemcpyDeviceToHost));
+  }
   if (ng) TRY_OR_CLEAN(cudaMemcpy(diag, dgp, ng * sizeof(double), cudaMemcpyDeviceToHost));
   if (nevalF) TRY_OR_CLEAN(cudaMemcpy(nevalF, df, (size_t)c.n_chains * sizeof(uint64_t), cudaMemcpyDeviceToHost));
   if (nevalB) TRY_OR_CLEAN(cudaMemcpy(nevalB, db, (size_t)c.n_chains * sizeof(uint64_t), cudaMemcpyDeviceToHost));

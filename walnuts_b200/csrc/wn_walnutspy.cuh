@@ -32,6 +32,8 @@ struct RunParams {
   double* state;        // [n_chains, d]
   double* draws;        // [n_iter, n_chains, dg] or null
   double* diag;         // [n_iter, n_chains, 24] or null
+  double* orbit_min;    // [n_iter, n_chains, dg] or null: recordOrbitStats (WALNUTS.py:182-184,274-276,...)
+  double* orbit_max;
   unsigned long long* nevalF;  // [n_chains] or null
   unsigned long long* nevalB;
   unsigned long long* totals;  // [2] grid totals (forward, backward)
@@ -52,7 +54,7 @@ enum { PH_FWD = 0, PH_REDO = 1, PH_BWD = 2 };
 enum { ST_CHAIN = 0, ST_ITER, ST_LEVEL, ST_MACRO, ST_PASS_END, ST_LEAF, ST_LEVEL_END, ST_ITER_END, ST_RUN, ST_EXIT };
 
 // scratch vector ids
-enum { V_PARK_Q = 0, V_PARK_V = 1, V_PARK_G = 2, V_PROP0 = 3, V_PROP1 = 4, V_STACK = 5 };  // stack: 5 + 2*lvl (+1 for v)
+enum { V_PARK_Q = 0, V_PARK_V = 1, V_PARK_G = 2, V_PROP0 = 3, V_PROP1 = 4, V_OMIN = 5, V_OMAX = 6, V_STACK = 7 };  // stack: 7 + 2*lvl (+1 for v)
 __host__ __device__ inline int scratch_vectors(int M) { return V_STACK + 2 * (M + 1); }
 
 #define WN_LOG_ZERO (-700.0)
@@ -461,6 +463,7 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
             *sc(V_PARK_V, e2) = make_double2(v[2 * e2], v[2 * e2 + 1]);
             *sc(V_PARK_G, e2) = make_double2(g[2 * e2], g[2 * e2 + 1]);
             *sc(V_PROP0, e2) = qq;
+            if (P.orbit_min) { *sc(V_OMIN, e2) = qq; *sc(V_OMAX, e2) = qq; }   // :274-276
           }
           C.propCur = 0;
           C.lwtSum0 = 0.0; C.lwtSum1 = 0.0;
@@ -746,6 +749,19 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
             C.L_ = idx;
             C.indexStat = side ? -tl : tl;
           }
+          if (P.orbit_min) {
+#pragma unroll
+            for (int e2 = 0; e2 < E2; ++e2) {
+              double2 lo = *sc(V_OMIN, e2), hi = *sc(V_OMAX, e2);
+              // np.minimum / np.maximum propagate NaN
+              lo.x = (q[2 * e2] < lo.x || q[2 * e2] != q[2 * e2]) ? q[2 * e2] : lo.x;
+              lo.y = (q[2 * e2 + 1] < lo.y || q[2 * e2 + 1] != q[2 * e2 + 1]) ? q[2 * e2 + 1] : lo.y;
+              hi.x = (q[2 * e2] > hi.x || q[2 * e2] != q[2 * e2]) ? q[2 * e2] : hi.x;
+              hi.y = (q[2 * e2 + 1] > hi.y || q[2 * e2 + 1] != q[2 * e2 + 1]) ? q[2 * e2 + 1] : hi.y;
+              *sc(V_OMIN, e2) = lo;
+              *sc(V_OMAX, e2) = hi;
+            }
+          }
           bool sub = false;
           if (level > 0) {
             const double xi = C.xi;
@@ -825,6 +841,15 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
             for (int e = 0; e < E; ++e) {
               const int j = target.coord(e, t);
               if (j < P.dg) P.draws[row * P.dg + j] = q[e];
+            }
+          }
+          if (P.orbit_min) {
+#pragma unroll
+            for (int e2 = 0; e2 < E2; ++e2) {
+              const double2 lo = *sc(V_OMIN, e2), hi = *sc(V_OMAX, e2);
+              const int j0 = target.coord(2 * e2, t), j1 = target.coord(2 * e2 + 1, t);
+              if (j0 < P.dg) { P.orbit_min[row * P.dg + j0] = lo.x; P.orbit_max[row * P.dg + j0] = hi.x; }
+              if (j1 < P.dg) { P.orbit_min[row * P.dg + j1] = lo.y; P.orbit_max[row * P.dg + j1] = hi.y; }
             }
           }
           const unsigned long long nF = C.nF, nB = C.nB;

@@ -115,17 +115,20 @@ class ChainBatch:
         return out
 
     # -- sampling ---------------------------------------------------------------------------
-    def run(self, n_iter, draws=True, diag=False, nevals=True):
-        """Host-buffer path (H2D/D2H inside): returns dict(draws, diag, nevalF, nevalB)."""
+    def run(self, n_iter, draws=True, diag=False, nevals=True, orbit_stats=False):
+        """Host-buffer path (H2D/D2H inside): returns dict(draws, diag, nevalF, nevalB[, orbit_min, orbit_max])."""
         n_iter = int(n_iter)
         out = {}
         d_arr = np.empty((n_iter, self.n_chains, self.dg)) if draws and self.dg > 0 else None
         g_arr = np.empty((n_iter, self.n_chains, _ffi.DIAG_COLS)) if diag else None
         f_arr = np.zeros(self.n_chains, dtype=np.uint64) if nevals else None
         b_arr = np.zeros(self.n_chains, dtype=np.uint64) if nevals else None
-        rc = self._lib.wn_run(self._h, n_iter, _ptr(d_arr)[0], _ptr(g_arr)[0], _ptr(f_arr)[0], _ptr(b_arr)[0], 0)
+        lo = np.empty((n_iter, self.n_chains, self.dg)) if orbit_stats else None
+        hi = np.empty((n_iter, self.n_chains, self.dg)) if orbit_stats else None
+        rc = self._lib.wn_run_stats(self._h, n_iter, _ptr(d_arr)[0], _ptr(g_arr)[0], _ptr(f_arr)[0], _ptr(b_arr)[0],
+                                    _ptr(lo)[0], _ptr(hi)[0], 0)
         self._check(rc, "wn_run")
-        out.update(draws=d_arr, diag=g_arr, nevalF=f_arr, nevalB=b_arr)
+        out.update(draws=d_arr, diag=g_arr, nevalF=f_arr, nevalB=b_arr, orbit_min=lo, orbit_max=hi)
         return out
 
     def run_device(self, n_iter, draws=None, diag=None, nevalF=None, nevalB=None, sync=True):
