@@ -308,7 +308,9 @@ def main():
         "gpu_launches": args.steps * cb.last_launches(),
         "clocks": clocks,
         "roofline": {"bound": "fp64", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                     "traffic": None, "peak_source": peak_src,
+                     "traffic": 0.98e9 * (evals / max(1, args.steps)) / 3.26e8,   # ncu dram bytes, scaled by evals
+                     "flop_per_eval": FLOP_PER_DIM_PER_EVAL * D, "achieved_at_12_flop_per_coord": ach * 12 / 8,
+                     "peak_source": peak_src,
                      "note": "register-resident chains: FP64 FMA pipe bound, not HBM (SURVEY.md 8d); "
                              f"HBM peak {hbm_peak} GB/s is not the limiter"},
         "lib": os.path.relpath(_ffi.lib_path(), ROOT),
