@@ -147,12 +147,24 @@ static bool pick_plan(const wn_config& c, bool adapt, LaunchPlan& p) {
       }
       return pick_generic<DiagT>(pkg, c.d, p);
     }
-    case WN_TARGET_FUNNEL: return pick_warp<FunnelT>(pkg, c.d, p);
+    case WN_TARGET_FUNNEL:
+      if (pkg == 0 && c.d <= 12) {   // BASELINE config 3 (funnel10): one thread per chain
+        const char* v = getenv("WN_VARIANT");
+        if (v && atoi(v) == 1) p = plan_wpy<FunnelT, 1, 6, 128, 3>();
+        else p = plan_wpy<FunnelT, 1, 6, 128, 1>();
+        return true;
+      }
+      return pick_warp<FunnelT>(pkg, c.d, p);
     case WN_TARGET_FUNNEL_PKG: return pick_warp<FunnelPkgT>(pkg, c.d, p);
-    case WN_TARGET_LOGREG:
+    case WN_TARGET_LOGREG: {
       if (c.d > 128) return false;
-      p = plan_for<LogRegT, 32, 2, 256>(pkg);
+      // block-cooperative gradient (8 chains per CTA share every load of X) for the plain WALNUTSpy kernel;
+      // the per-warp version serves package mode / warm-up adaptation and WN_VARIANT=1 (comparison)
+      const char* v = getenv("WN_VARIANT");
+      if (pkg == 0 && !(v && atoi(v) == 1)) p = plan_wpy<LogRegCoopT, 32, 2, 256>();
+      else p = plan_for<LogRegT, 32, 2, 256>(pkg);
       return true;
+    }
     case WN_TARGET_STOCK_WATSON: {
       // d = 3T; thread t owns B consecutive time steps: T <= G*B
       if (c.d % 3 != 0) return false;

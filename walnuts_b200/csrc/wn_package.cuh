@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(NT, MINB) package_kernel(const __grid_constant
   using Grp = Group<G>;
   using Target = TargetTT<G, E2>;
 
-  extern __shared__ double smem[];
+  extern __shared__ __align__(16) double smem[];
   double* ck = smem;                   // checkpoint [3*E][NT]
   double* red = smem + 3 * E * NT;
   __shared__ uint32_t sh_bcast;

@@ -37,6 +37,7 @@ struct DiagGaussT {
   // intermediate energy is provably finite, so the intermediate steps may skip the two energy FMAs per
   // coordinate; if the bound is ever violated the sampler re-runs the pass with per-step energies.
   static constexpr bool LAZY_ENERGY = true;
+  static constexpr bool COOP = false;
   __host__ __device__ static constexpr int smem_doubles(int) { return 0; }
   __device__ __forceinline__ int coord(int e, int t) const { return coord_of<G>(e, t); }
   double s[UNIT ? 1 : E];
@@ -89,6 +90,7 @@ struct FunnelT {
   static constexpr bool PAIR_LAYOUT = true;
   static constexpr bool BLOCK_LOCKSTEP = false;
   static constexpr bool LAZY_ENERGY = false;
+  static constexpr bool COOP = false;
   __host__ __device__ static constexpr int smem_doubles(int) { return 0; }
   __device__ __forceinline__ int coord(int e, int t) const { return coord_of<G>(e, t); }
   static_assert(G <= 32, "funnel target needs the chain inside one warp");
@@ -133,6 +135,7 @@ struct FunnelPkgT {
   static constexpr bool PAIR_LAYOUT = true;
   static constexpr bool BLOCK_LOCKSTEP = false;
   static constexpr bool LAZY_ENERGY = false;
+  static constexpr bool COOP = false;
   __host__ __device__ static constexpr int smem_doubles(int) { return 0; }
   __device__ __forceinline__ int coord(int e, int t) const { return coord_of<G>(e, t); }
   static_assert(G <= 32, "funnel target needs the chain inside one warp");
@@ -170,6 +173,7 @@ struct CorrGaussT {
   static constexpr bool PAIR_LAYOUT = true;
   static constexpr bool BLOCK_LOCKSTEP = false;
   static constexpr bool LAZY_ENERGY = false;
+  static constexpr bool COOP = false;
   __host__ __device__ static constexpr int smem_doubles(int) { return 0; }
   __device__ __forceinline__ int coord(int e, int t) const { return coord_of<G>(e, t); }
   static_assert(G == 1 && E2 == 1, "corr_gauss is 2-d");
@@ -203,6 +207,7 @@ struct StockWatsonT {
   static constexpr bool PAIR_LAYOUT = false;
   static constexpr bool BLOCK_LOCKSTEP = false;
   static constexpr bool LAZY_ENERGY = false;
+  static constexpr bool COOP = false;
   __host__ __device__ static constexpr int smem_doubles(int) { return 0; }
   static constexpr int WARPS = (G + 31) / 32;
   static_assert(3 * B + 2 == E, "E must be 3B + 2");
@@ -388,6 +393,7 @@ struct LogRegT {
   static constexpr bool PAIR_LAYOUT = true;
   static constexpr bool BLOCK_LOCKSTEP = true;
   static constexpr bool LAZY_ENERGY = false;
+  static constexpr bool COOP = false;
   static constexpr int RT = 128, RJ = RT / 32, PMAX = 2 * G * E2;
   static_assert(G == 32, "logistic regression target: one warp per chain");
   __host__ __device__ static constexpr int smem_doubles(int NT) { return (NT / 32) * (PMAX + RT); }
@@ -470,6 +476,268 @@ struct LogRegT {
       qq = fma(q[e], q[e], qq);
     }
     return lp - 0.5 * itau2 * qq;
+  }
+};
+
+}  // namespace wn
+
+namespace wn {
+
+// ---- T4, block-cooperative version: the chains of a CTA evaluate their gradients TOGETHER --------------------
+// 8 chains per CTA of 256 threads (one warp owns one chain's coordinates, as in LogRegT).  Every trip of the
+// sampler's loop the active chains publish beta to shared memory; then ALL 256 threads stream the rows once:
+//   phase 1 (4 rows per thread): eta_n^c = x_n . beta^c for the 8 chains  (X^T coalesced over rows; 32 FMA per
+//                                4 loads + 4 shared broadcasts), r_n^c = y_n - sigmoid(eta_n^c),
+//                                lp^c += y_n eta - log(1+e^eta) only for chains at the end of a pass -> shared r tile
+//   phase 2 (lane = 4 coordinates, warp = row stream): acc[k][c] += X[n][k] r_n^c            (32 FMA per row)
+// so every element of X is loaded once per CTA trip instead of once per chain.  Deterministic: partial sums are
+// combined in a fixed order (no atomics).
+template <int G, int E2>
+struct LogRegCoopT {
+  static constexpr int E = 2 * E2;
+  static constexpr bool PAIR_LAYOUT = true;
+  static constexpr bool BLOCK_LOCKSTEP = false;   // the cooperative evaluation has its own barriers
+  static constexpr bool LAZY_ENERGY = false;
+  static constexpr bool COOP = true;
+  static constexpr int NTC = 256, C = 8, PMAX = 128, RPT = 4, RT = NTC * RPT;
+  static_assert(G == 32 && E2 == 2, "cooperative logistic regression: one warp per chain, P <= 128");
+  // Staging ring: S stages of STG doubles, filled by bulk async copies (TMA engine) that complete on a
+  // "full" mbarrier per stage; consumers release a stage by arriving on its "empty" mbarrier, and the
+  // producer (thread 0) refills it S-1 chunks ahead -- across the phase-1 / phase-2 / row-tile boundaries.
+  // Chunk stream of one evaluation: per row tile, P chunks "coordinate k of X^T for the tile's rows"
+  // followed by ceil(rows/8) chunks "8 rows of X".
+  // Measured on B200: with only 32 FMA per thread between two barrier operations the
+  // per-chunk mbarrier wait/arrive costs more than the L2 latency it hides (0.99e5 vs 1.37e5 evals/s with plain
+  // read-only loads and 16 loads in flight per thread), so the staging ring is compiled out by default.
+  static constexpr bool USE_BULK = false;
+  static constexpr int S = 8, STG = 1024, RC = 8;
+  // shared: bs[PMAX][C] | rs[RT][C] | gs[C][PMAX] | part[8][PMAX][4] | lps[8 warps][C] | act[C] | need[C]
+  //         | full[S] | empty[S] | stage[S][STG]
+  __host__ __device__ static constexpr int smem_doubles(int) {
+    return PMAX * C + RT * C + C * PMAX + 8 * PMAX * 4 + 8 * C + 2 * C + 2 * S + (USE_BULK ? S * STG : 0);
+  }
+  const double *X, *XT, *y;
+  int N, P;
+  double itau2;
+  double *bs, *rs, *gs, *part, *lps, *act, *need, *stage;
+  uint64_t *full, *empty;
+  bool bulk;      // 16-byte alignment of every staged chunk holds (N and P even)
+  __device__ __forceinline__ int coord(int e, int t) const { return coord_of<G>(e, t); }
+  __device__ __forceinline__ void init(const TargetParams& tp, int d, int, double* tsm) {
+    X = tp.p0; y = tp.p1; XT = tp.p2; N = tp.n0; P = d; itau2 = tp.c0;
+    bs = tsm; rs = bs + PMAX * C; gs = rs + RT * C; part = gs + C * PMAX; lps = part + 8 * PMAX * 4; act = lps + 8 * C;
+    need = act + C;
+    full = reinterpret_cast<uint64_t*>(need + C);
+    empty = full + S;
+    stage = need + C + 2 * S;
+    bulk = USE_BULK && ((N & 1) == 0) && ((P & 1) == 0);
+    if (USE_BULK && threadIdx.x == 0) {
+      for (int i = 0; i < S; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], NTC); }
+      mbar_fence_init();
+    }
+    __syncthreads();
+  }
+  // not used by COOP kernels (the generic protocol entry point)
+  __device__ __forceinline__ double lp_grad(const double (&)[E], double (&)[E], double*, int&) const { return 0.0; }
+
+  // need_lp: the energy of this step is consumed (last step of a pass).  For this target a non-finite
+  // intermediate energy implies a non-finite state, which persists to the end of the pass, so skipping the
+  // log-likelihood of intermediate steps does not change all(isfinite(Hams)) (adaptiveIntegrators.py:92).
+  __device__ __forceinline__ void publish(const double (&q)[E], bool active, bool need_lp) const {
+    const int w = threadIdx.x >> 5, t = threadIdx.x & 31;
+#pragma unroll
+    for (int e = 0; e < E; ++e) bs[coord_of<G>(e, t) * C + w] = active ? q[e] : 0.0;
+    if (t == 0) { act[w] = active ? 1.0 : 0.0; need[w] = (active && need_lp) ? 1.0 : 0.0; }
+  }
+
+  // `gch`: number of chunks consumed so far by this CTA (kept by the caller across evaluations); chunk g
+  // lives in stage g % S and completes phase (g / S) & 1 of that stage's barriers.
+  __device__ __forceinline__ void coop_eval(uint32_t& gch) const {
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    bool any = false;
+    bool nl[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) { any = any || (act[c] != 0.0); nl[c] = need[c] != 0.0; }
+    if (!any) return;
+    double acc[4][C];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int c = 0; c < C; ++c) acc[j][c] = 0.0;
+    double lp[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) lp[c] = 0.0;
+    const int k4 = 4 * lane;
+
+    // ---- producer cursor (thread 0 only): next chunk to issue ----
+    uint32_t pg = gch;            // global index of the next chunk to issue
+    int pn0 = 0, pi = 0;          // its row tile and index inside the tile's chunk list
+    auto produce = [&]() {        // issue one chunk if any is left in this evaluation
+      if (pn0 >= N) return;
+      const int nrows = min(RT, N - pn0);
+      const int st_ = pg % S;
+      if (pg >= (uint32_t)S) mbar_wait(&empty[st_], ((pg / S) & 1u) ^ 1u);   // previous use released by all
+      double* dst = stage + st_ * STG;
+      if (pi < P) {
+        mbar_expect_tx(&full[st_], (uint32_t)(nrows * 8));
+        bulk_g2s(dst, XT + (size_t)pi * N + pn0, (uint32_t)(nrows * 8), &full[st_]);
+      } else {
+        const int r0 = (pi - P) * RC, rn = min(RC, nrows - r0);
+        mbar_expect_tx(&full[st_], (uint32_t)(rn * P * 8));
+        bulk_g2s(dst, X + (size_t)(pn0 + r0) * P, (uint32_t)(rn * P * 8), &full[st_]);
+      }
+      ++pg;
+      ++pi;
+      if (pi >= P + (nrows + RC - 1) / RC) { pi = 0; pn0 += RT; }
+    };
+    if (bulk && tid == 0) {
+      for (int i = 0; i < S - 1; ++i) produce();
+    }
+    auto consume_begin = [&]() -> const double* {
+      if (tid == 0) produce();                       // keep S-1 chunks in flight
+      const int st_ = gch % S;
+      mbar_wait(&full[st_], (gch / S) & 1u);
+      return stage + st_ * STG;
+    };
+    auto consume_end = [&]() {
+      mbar_arrive(&empty[gch % S]);
+      ++gch;
+    };
+
+    for (int n0 = 0; n0 < N; n0 += RT) {
+      const int nrows = min(RT, N - n0);
+      // ---- phase 1: rows n0 + tid + 256 j, j < 4 ----
+      {
+        double eta[RPT][C];
+#pragma unroll
+        for (int j = 0; j < RPT; ++j)
+#pragma unroll
+          for (int c = 0; c < C; ++c) eta[j][c] = 0.0;
+        bool in[RPT];
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) in[j] = tid + NTC * j < nrows;
+#pragma unroll 2
+        for (int k = 0; k < P; ++k) {
+          double x[RPT];
+          if (bulk) {
+            const double* sb = consume_begin();
+#pragma unroll
+            for (int j = 0; j < RPT; ++j) x[j] = in[j] ? sb[tid + NTC * j] : 0.0;
+            consume_end();
+          } else {
+#pragma unroll
+            for (int j = 0; j < RPT; ++j) x[j] = in[j] ? __ldg(XT + (size_t)k * N + n0 + tid + NTC * j) : 0.0;
+          }
+          const double2* b2 = reinterpret_cast<const double2*>(bs + k * C);
+#pragma unroll
+          for (int c2 = 0; c2 < C / 2; ++c2) {
+            const double2 bb = b2[c2];
+#pragma unroll
+            for (int j = 0; j < RPT; ++j) {
+              eta[j][2 * c2] = fma(x[j], bb.x, eta[j][2 * c2]);
+              eta[j][2 * c2 + 1] = fma(x[j], bb.y, eta[j][2 * c2 + 1]);
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) {
+          const int n = n0 + tid + NTC * j;
+          const double yy = in[j] ? __ldg(y + n) : 0.0;
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            const double et = eta[j][c];
+            const double ex = exp(-fabs(et));
+            const double inv = 1.0 / (1.0 + ex);
+            const double sig = (et >= 0.0) ? inv : ex * inv;
+            eta[j][c] = in[j] ? (yy - sig) : 0.0;                                  // residual
+            if (nl[c] && in[j]) lp[c] += yy * et - (fmax(et, 0.0) + log1p(ex));
+          }
+          double2* r2 = reinterpret_cast<double2*>(rs + (tid + NTC * j) * C);
+#pragma unroll
+          for (int c2 = 0; c2 < C / 2; ++c2) r2[c2] = make_double2(eta[j][2 * c2], eta[j][2 * c2 + 1]);
+        }
+      }
+      __syncthreads();
+      // ---- phase 2: chunks of 8 rows; warp w takes row w of the chunk; lane owns coordinates 4*lane .. +3 ----
+      {
+        const int nchunk = (nrows + RC - 1) / RC;
+#pragma unroll 4
+        for (int ch = 0; ch < nchunk; ++ch) {
+          const int i = ch * RC + w;                 // row inside the tile
+          double x[4];
+          if (bulk) {
+            const double* sb = consume_begin();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) x[j] = (i < nrows && k4 + j < P) ? sb[w * P + k4 + j] : 0.0;
+            consume_end();
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) x[j] = (i < nrows && k4 + j < P) ? __ldg(X + (size_t)(n0 + i) * P + k4 + j) : 0.0;
+          }
+          if (i < nrows) {
+            const double2* r2 = reinterpret_cast<const double2*>(rs + i * C);
+#pragma unroll
+            for (int c2 = 0; c2 < C / 2; ++c2) {
+              const double2 r = r2[c2];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                acc[j][2 * c2] = fma(x[j], r.x, acc[j][2 * c2]);
+                acc[j][2 * c2 + 1] = fma(x[j], r.y, acc[j][2 * c2 + 1]);
+              }
+            }
+          }
+        }
+      }
+      __syncthreads();
+    }
+    // ---- combine the 8 row streams (fixed order), 4 chains per round ----
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) part[(w * PMAX + k4 + j) * 4 + c] = acc[j][4 * half + c];
+      __syncthreads();
+      {
+        const int k = tid & (PMAX - 1), cp = tid >> 7;          // 2 chains per thread
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          const int c = 2 * cp + cc;
+          double s = 0.0;
+#pragma unroll
+          for (int ww = 0; ww < 8; ++ww) s += part[(ww * PMAX + k) * 4 + c];
+          gs[(4 * half + c) * PMAX + k] = s;
+        }
+      }
+      __syncthreads();
+    }
+    // ---- log-likelihood: lanes -> warp (butterfly), warps -> block (fixed order in collect) ----
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      double v = lp[c];
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+      if (lane == 0) lps[w * C + c] = v;
+    }
+    __syncthreads();
+  }
+
+  // gradient of this warp's chain (after coop_eval); returns this thread's partial of lp
+  __device__ __forceinline__ double collect(const double (&q)[E], double (&g)[E]) const {
+    const int w = threadIdx.x >> 5, t = threadIdx.x & 31;
+    double qq = 0.0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int k = coord_of<G>(e, t);
+      g[e] = (k < P) ? fma(-itau2, q[e], gs[w * PMAX + k]) : 0.0;
+      qq = fma(q[e], q[e], qq);
+    }
+    double lp = -0.5 * itau2 * qq;
+    if (t == 0) {
+#pragma unroll
+      for (int ww = 0; ww < 8; ++ww) lp += lps[ww * C + w];
+    }
+    return lp;
   }
 };
 

@@ -15,6 +15,8 @@
 //   global    : slot-indexed scratch (other orbit end, two proposal slots, left-end stack of <= M
 //               pending dyadic levels) -- indexed by resident slot, not by chain, so it stays L2-sized.
 #pragma once
+#include <type_traits>
+
 #include "wn_common.cuh"
 #include "wn_targets.cuh"
 
@@ -50,8 +52,8 @@ struct RunParams {
 #define WN_ADAPT_STRIDE 16
 
 enum { KIND_FIXED = 0, KIND_D = 1, KIND_R2P = 2 };
-enum { PH_FWD = 0, PH_REDO = 1, PH_BWD = 2 };
-enum { ST_CHAIN = 0, ST_ITER, ST_LEVEL, ST_MACRO, ST_PASS_END, ST_LEAF, ST_LEVEL_END, ST_ITER_END, ST_RUN, ST_EXIT };
+enum { PH_FWD = 0, PH_REDO = 1, PH_BWD = 2, PH_INIT = 3 };
+enum { ST_CHAIN = 0, ST_ITER, ST_ITER2, ST_LEVEL, ST_MACRO, ST_PASS_END, ST_LEAF, ST_LEVEL_END, ST_ITER_END, ST_RUN, ST_EXIT };
 
 // scratch vector ids
 enum { V_PARK_Q = 0, V_PARK_V = 1, V_PARK_G = 2, V_PROP0 = 3, V_PROP1 = 4, V_OMIN = 5, V_OMAX = 6, V_STACK = 7 };  // stack: 7 + 2*lvl (+1 for v)
@@ -88,13 +90,17 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
   using Grp = Group<G>;
   using Target = TargetTT<G, E2>;
 
-  extern __shared__ double smem[];
+  extern __shared__ __align__(16) double smem[];
   double* ck = smem;                       // checkpoint: [3*E][NT]
   double* red = smem + 3 * E * NT;         // reduction scratch (G > 32)
   __shared__ uint32_t sh_bcast;
   __shared__ Ctl sh_ctl[(G >= 32) ? NT / 32 : 1];
-  Ctl loc_ctl;                             // used only when several chains share a warp (G < 32)
-  volatile Ctl& C = (G >= 32) ? sh_ctl[threadIdx.x >> 5] : loc_ctl;
+  // G >= 32: one copy per warp in shared memory (volatile: every lane stores the same value, then reads it
+  // back).  G < 32: several chains share a warp, each thread keeps a private copy which the compiler is free
+  // to hold in registers / spill to local memory as it sees fit.
+  Ctl loc_ctl;
+  using CtlRef = typename std::conditional<(G >= 32), volatile Ctl&, Ctl&>::type;
+  CtlRef C = *((G >= 32) ? &sh_ctl[threadIdx.x >> 5] : &loc_ctl);
 
   const int tid = threadIdx.x;
   const int t = tid % G;
@@ -326,6 +332,7 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
   };
   constexpr int LAZY_LIMIT = (1023 + 300) << 20;
 
+  uint32_t coop_phase = 0;   // COOP targets: phase bits of the staging mbarriers
   int st = ST_CHAIN;
   for (;;) {
     if constexpr (Target::BLOCK_LOCKSTEP) {
@@ -334,7 +341,34 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
       if (__syncthreads_and(st == ST_EXIT)) break;
     }
     // =============================== hot: leapfrog micro-steps ==================================
-    if (st == ST_RUN) {
+    if constexpr (Target::COOP) {
+      // block-cooperative gradient: every chain of the CTA that is in a pass takes ONE micro-step per trip;
+      // the gradient of all of them is evaluated together by all threads (shared data streamed once)
+      const bool act = (st == ST_RUN);
+      if (act) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          v[e] = fma(ha, g[e], v[e]);
+          q[e] = fma(hh, v[e], q[e]);
+        }
+      }
+      target.publish(q, act, steps_left == 1u);
+      if (__syncthreads_and(st == ST_EXIT)) break;      // barrier + exit vote
+      target.coop_eval(coop_phase);
+      if (act) {
+        const double lpp = target.collect(q, g);
+        double ke = 0.0;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          v[e] = fma(ha, g[e], v[e]);
+          ke = fma(v[e], v[e], ke);
+        }
+        hp = fma(0.5, ke, -lpp);
+        expmax = max(expmax, __double2hiint(hp) & 0x7ff00000);
+        if (--steps_left != 0u) continue;
+        st = ST_PASS_END;
+      }
+    } else if (st == ST_RUN) {
       if (ADAPT && trackH) {   // warm-up: every step's energy is needed for igrConst
         micro_step();
 #pragma unroll
@@ -448,12 +482,28 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
             }
 #pragma unroll
             for (int e = 0; e < E; ++e) ke = fma(v[e], v[e], ke);
+            if constexpr (Target::COOP) {
+              // the gradient at the current state (:249) is requested as a zero-length pass: h = 0 leaves
+              // (q, v) untouched and the cooperative evaluation fills g and the energy partial
+#pragma unroll
+              for (int e = 0; e < E; ++e) g[e] = 0.0;
+              C.phase = PH_INIT;
+              rsearch = false;
+              rh = 0.0;
+              start_pass(0);
+              st = ST_RUN;
+              break;
+            }
             const double lpp = target.lp_grad(q, g, red, parity);        // :249
             x[0] = fma(0.5, ke, -lpp);
           }
           Grp::template sum<1>(x, red, parity);
-          const double H0 = x[0];                                         // :256
-          C.H0 = H0;
+          st = ST_ITER2;
+          C.H0 = x[0];
+          break;
+        }
+        case ST_ITER2: {  // second half of the per-iteration setup (after the gradient at the current state)
+          const double H0 = C.H0;                                         // :256
           C.endH0 = H0;
           C.endH1 = H0;
 #pragma unroll
@@ -573,6 +623,11 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
             }
           }
           const int phase = C.phase;
+          if (Target::COOP && phase == PH_INIT) {   // gradient at the current state arrived: H0 = Hend
+            C.H0 = Hend;
+            st = ST_ITER2;
+            break;
+          }
           if (rsearch) {   // leave the fast path: write the search state back
             C.c = rc;
             if (phase == PH_FWD) C.nF = C.nF + rEv; else C.nB = C.nB + rEv;
@@ -953,7 +1008,7 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
       }
     }
     if (st == ST_EXIT) {
-      if constexpr (Target::BLOCK_LOCKSTEP) continue;
+      if constexpr (Target::BLOCK_LOCKSTEP || Target::COOP) continue;   // keep serving the block's barriers
       break;
     }
   }
