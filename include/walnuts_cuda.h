@@ -72,7 +72,9 @@ typedef struct wn_config {
   int32_t dg;          /* leading coordinates stored per draw (generated = q[0:dg])      */
   int32_t M;           /* max doublings: WALNUTS(M=) / walnuts(max_nuts_depth=)          */
   int32_t minC, maxC;  /* integratorAuxPar.minC / maxC, adaptiveIntegrators.py:36-44     */
-  int32_t compat;      /* PACKAGE mode: 1 = reproduce reference defects B3/B5*/
+  int32_t compat;      /* 1 = reproduce the reference's latent defects bit-for-bit: PACKAGE mode B3/B5
+                          (walnuts.py:194,242-245,272), WALNUTSPY mode A14(i) (WALNUTS.py:420 vs :443-459,
+                          biases the funnel); 0 = corrected semantics           */
   int32_t reserved0;
   double H0;           /* macro step: WALNUTS(H0=) / walnuts(macro_step=)                */
   double jitter;       /* WALNUTS(stepSizeRandScale=), WALNUTS.py:298,395                */

@@ -191,7 +191,8 @@ static int ctz32(uint32_t x) { return __builtin_ctz(x); }
 /* One chain: n_iter transitions.  draws [n_iter, d], diag [n_iter, 24] (either may be NULL). */
 int wno_run_chain(int target, int kind, int d, const double* inv_var, const double* q0, double H, double delta,
                   double jitter, int M, int minC, int maxC, double p0, uint64_t seed, uint32_t chain,
-                  uint32_t first_iter, int n_iter, double* draws, double* diag, double* q_out, uint64_t* nevals) {
+                  uint32_t first_iter, int n_iter, double* draws, double* diag, double* q_out, uint64_t* nevals,
+                  int compat) {
   target_t t = {target, d, inv_var};
   rng_t rng = {(uint32_t)seed, (uint32_t)(seed >> 32), chain, 0, 0};
   double* buf = (double*)malloc(sizeof(double) * d * (size_t)(3 + 3 + 3 + 6 + 2 + 2 * (M + 2)));
@@ -254,7 +255,7 @@ int wno_run_chain(int target, int kind, int d, const double* inv_var, const doub
         if (o.H != o.H) sHnan = 1; else { if (o.H > sHmax) sHmax = o.H; if (o.H < sHmin) sHmin = o.H; }
         if (!isfinite(o.H)) { forced = 1; if (i == 0 || (n & 1u)) stopCode = 999; break; }
         if (i == 0) lwtSum[side] = o.lwt;
-        else if (!(side == 1 && !(n & 1u))) lwtSum[side] += o.lwt;       /* quirk A14(i) */
+        else if (!compat || !(side == 1 && !(n & 1u))) lwtSum[side] += o.lwt;       /* quirk A14(i) */
         const double Wnew = exp(-o.H + H0 + lwtSum[side]);
         const double* eq = ends[side].q; const double* ev = ends[side].v;
         if (i == 0) {
@@ -317,7 +318,7 @@ int wno_run_chain(int target, int kind, int d, const double* inv_var, const doub
 /* Many independent chains on `threads` host threads (pthreads, dynamic chain queue); q [n_chains, d] in/out. */
 #include <pthread.h>
 typedef struct {
-  int target, kind, d, n_chains, M, minC, maxC, n_iter;
+  int target, kind, d, n_chains, M, minC, maxC, n_iter, compat;
   const double* inv_var;
   double* q;
   double H, delta, jitter, p0;
@@ -339,7 +340,7 @@ static void* many_worker(void* arg) {
     uint64_t ne = 0;
     err |= wno_run_chain(m->target, m->kind, m->d, m->inv_var, m->q + (size_t)c * m->d, m->H, m->delta, m->jitter,
                          m->M, m->minC, m->maxC, m->p0, m->seed, m->chain0 + (uint32_t)c, m->first_iter, m->n_iter,
-                         NULL, NULL, m->q + (size_t)c * m->d, &ne);
+                         NULL, NULL, m->q + (size_t)c * m->d, &ne, m->compat);
     tot += ne;
   }
   pthread_mutex_lock(&m->mu);
@@ -351,8 +352,8 @@ static void* many_worker(void* arg) {
 
 int wno_run_many(int target, int kind, int d, const double* inv_var, double* q, int n_chains, double H, double delta,
                  double jitter, int M, int minC, int maxC, double p0, uint64_t seed, uint32_t chain0,
-                 uint32_t first_iter, int n_iter, int threads, uint64_t* nevals_total) {
-  many_t m = {target, kind, d, n_chains, M, minC, maxC, n_iter, inv_var, q, H, delta, jitter, p0, seed, chain0,
+                 uint32_t first_iter, int n_iter, int threads, uint64_t* nevals_total, int compat) {
+  many_t m = {target, kind, d, n_chains, M, minC, maxC, n_iter, compat, inv_var, q, H, delta, jitter, p0, seed, chain0,
               first_iter, 0, 0, 0, PTHREAD_MUTEX_INITIALIZER};
   if (threads < 1) threads = 1;
   pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)threads);

@@ -26,7 +26,7 @@ def _dp(a):
 
 
 def run_chain(target, integrator, q0, H, delta, M, n_iter, seed, chain, minC=0, maxC=10, inv_var=None, jitter=0.2,
-              p0=2.0 / 3.0, first_iteration=1):
+              p0=2.0 / 3.0, first_iteration=1, compat=True):
     """One chain; returns (draws (n_iter, d), diag (n_iter, 24), nevals)."""
     lib = load()
     q0 = np.ascontiguousarray(q0, dtype=np.float64)
@@ -37,13 +37,13 @@ def run_chain(target, integrator, q0, H, delta, M, n_iter, seed, chain, minC=0, 
     ne = C.c_uint64()
     rc = lib.wno_run_chain(TARGET[target], KIND[integrator], d, _dp(iv), _dp(q0), C.c_double(H), C.c_double(delta),
                            C.c_double(jitter), M, minC, maxC, C.c_double(p0), C.c_uint64(seed), C.c_uint32(chain),
-                           C.c_uint32(first_iteration), n_iter, _dp(draws), _dp(diag), None, C.byref(ne))
+                           C.c_uint32(first_iteration), n_iter, _dp(draws), _dp(diag), None, C.byref(ne), int(compat))
     assert rc == 0
     return draws, diag, int(ne.value)
 
 
 def run_many(target, integrator, q, H, delta, M, n_iter, seed, threads, minC=0, maxC=10, inv_var=None, jitter=0.2,
-             p0=2.0 / 3.0, chain0=0, first_iteration=1):
+             p0=2.0 / 3.0, chain0=0, first_iteration=1, compat=True):
     """Many chains on `threads` host threads; q (n_chains, d) is advanced in place.  Returns total grad evals."""
     lib = load()
     assert q.flags.c_contiguous and q.dtype == np.float64
@@ -51,6 +51,6 @@ def run_many(target, integrator, q, H, delta, M, n_iter, seed, threads, minC=0, 
     ne = C.c_uint64()
     rc = lib.wno_run_many(TARGET[target], KIND[integrator], q.shape[1], _dp(iv), _dp(q), q.shape[0], C.c_double(H),
                           C.c_double(delta), C.c_double(jitter), M, minC, maxC, C.c_double(p0), C.c_uint64(seed),
-                          C.c_uint32(chain0), C.c_uint32(first_iteration), n_iter, threads, C.byref(ne))
+                          C.c_uint32(chain0), C.c_uint32(first_iteration), n_iter, threads, C.byref(ne), int(compat))
     assert rc == 0
     return int(ne.value)

@@ -127,7 +127,7 @@ def macro_step(kind, q, v, g, Ham0, h, xi, lpFun, delta, aux, rng):
     return dict(q=qO, v=xi * vO, grad=gO, H=HO, nF=nF, nB=nB, If=If, Ib=Ib, c=cSim, lwt=lwt, igrConst=igr)
 
 
-def transition(lpFun, qc, rng, kind, H, delta, M, aux, jitter=0.2, igr_sink=None, orbit=None):
+def transition(lpFun, qc, rng, kind, H, delta, M, aux, jitter=0.2, igr_sink=None, orbit=None, compat=True):
     """One WALNUTSpy iteration (WALNUTS.py:196-693).  Returns (q_next, diag[24])."""
     d = qc.size
     B = np.floor(rng.dir_uniform02(M)).astype(int)                      # :216
@@ -213,7 +213,7 @@ def transition(lpFun, qc, rng, kind, H, delta, M, aux, jitter=0.2, igr_sink=None
                 break
             if i == 0:
                 lwtSum[side] = o["lwt"]                                 # :321,354
-            elif not (side == 1 and n % 2 == 0):
+            elif not compat or not (side == 1 and n % 2 == 0):
                 lwtSum[side] += o["lwt"]    # quirk A14(i): :420 has no counterpart after :443-459
             Wnew = float(np.exp(-o["H"] + H0 + lwtSum[side]))           # :322,355,422,462,510,552
             if orbit is not None:       # :331-333,364-366,434-436,474-476,521-523,564-566
@@ -385,7 +385,7 @@ class NumpyGlobalRNG:
 def WALNUTS(lpFun, q0, generated=lambda q: q, integrator=FIXED, H0=0.2, stepSizeRandScale=0.2,
             delta0=0.05, numIter=2000, M=10, igrAux=None, rng=None, seed=0, chain=0,
             first_iteration=1, warmupIter=0, adaptH=False, adaptHtarget=0.8, adaptDelta=False,
-            adaptDeltaTarget=0.6, adaptDeltaQuantile=0.9, recordOrbitStats=False):
+            adaptDeltaTarget=0.6, adaptDeltaQuantile=0.9, recordOrbitStats=False, compat=True):
     """WALNUTSpy chain incl. the warm-up adaptation of H and delta (WALNUTS.py:136-147, 313, 701-712).
     Returns (samples (dg, numIter+1), diagnostics (numIter, 24)) like WALNUTS.py:724-727."""
     from . import philox
@@ -415,7 +415,7 @@ def WALNUTS(lpFun, q0, generated=lambda q: q, integrator=FIXED, H0=0.2, stepSize
         with np.errstate(all="ignore"):
             orb = {} if recordOrbitStats else None
             qc, diagnostics[it - 1] = transition(lpFun, qc, rng, integrator, H, delta, M, aux,
-                                                 jitter=stepSizeRandScale, igr_sink=sink, orbit=orb)
+                                                 jitter=stepSizeRandScale, igr_sink=sink, orbit=orb, compat=compat)
             if recordOrbitStats:
                 orbitMin[:, it - 1], orbitMax[:, it - 1] = orb["min"], orb["max"]
             samples[:, it] = generated(qc)

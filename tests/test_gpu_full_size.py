@@ -56,3 +56,58 @@ def test_c3_funnel_262144_chains_invariance(cuda_lib):
     dg = out["diag"]
     assert (dg[..., 19] != 999).all()                          # no numerical rejects from stationarity
     assert dg[..., 22].max() >= 3                              # micro-step halving really exercised
+
+
+def _check_moments(x, mean, var, kurt_excess=0.0, nse=4.0):
+    """x: (n_chains,) one draw per independent chain; exact MC standard errors for mean and variance."""
+    n = x.size
+    assert abs(x.mean() - mean) < nse * np.sqrt(var / n), (x.mean(), mean)
+    se_var = var * np.sqrt((2.0 + kurt_excess) / n)
+    assert abs(x.var() - var) < nse * se_var, (x.var(), var)
+
+
+@pytest.mark.parametrize("integrator", ["fixed", "D", "R2P"])
+def test_long_run_moments_corr_gauss_with_default_adaptation(cuda_lib, integrator):
+    """Long run from a fixed, atypical start through the drop-in WALNUTS(...) with the reference's default
+    warm-up adaptation: after warm-up the chains must reproduce the target's moments (corrGauss: unit
+    variances, correlation 0.5, targetDistr.py:25-31) within 4 Monte-Carlo standard errors across chains."""
+    import walnuts_b200 as wb
+    ig = {"fixed": wb.fixedLeapFrog, "D": wb.adaptLeapFrogD, "R2P": wb.adaptLeapFrogR2P}[integrator]
+    n = 8192
+    q0 = np.tile(np.array([3.0, -3.0]), (n, 1))
+    s, d = wb.WALNUTS(wb.targets.corrGauss, q0, integrator=ig, numIter=160, warmupIter=100, M=8, seed=17)
+    x = s[:, :, -1]                                   # last draw of every chain: independent across chains
+    _check_moments(x[:, 0], 0.0, 1.0)
+    _check_moments(x[:, 1], 0.0, 1.0)
+    rho = np.mean(x[:, 0] * x[:, 1])
+    assert abs(rho - 0.5) < 4.0 * np.sqrt((1 + 0.25) / n), rho       # var(xy) = 1 + rho^2
+    assert (d[:, -1, 19] != 999).all()
+
+
+@pytest.mark.parametrize("integrator", ["D", "R2P"])
+def test_long_run_moments_funnel(cuda_lib, integrator):
+    """funnel10 (targetDistr.py:74-78), mainFunnel.py settings (M=12, H0=0.3, delta0=0.3, R2P, fixed H/delta):
+    omega = q[0] ~ N(0, 9) and the standardised coordinates q_i exp(-omega/2) ~ N(0, 1).  The funnel mixes
+    slowly in omega (the paper runs 1e6 iterations), so the long run starts from exact target draws: any
+    non-invariance of the transition would accumulate over the 100 transitions.
+
+    Run with compat=False: the reference's defect A14(i) (the second leaf of a backward pair never adds its
+    log-weight, WALNUTS.py:420 vs :443-459) makes the reference itself drift on this target -- after 100
+    transitions omega has mean +0.07 (6 SE) and variance 8.65 (-7 SE) with 65 536 chains, identically on the
+    GPU (compat=True) and in the reference-pinned C oracle; with the log-weight added the moments hold."""
+    from walnuts_b200 import ChainBatch
+    n = 32768
+    rng = np.random.default_rng(31)
+    q0 = np.empty((n, 11))
+    q0[:, 0] = 3.0 * rng.standard_normal(n)
+    q0[:, 1:] = np.exp(0.5 * q0[:, :1]) * rng.standard_normal((n, 10))
+    with ChainBatch("funnel", 11, n, integrator=integrator, H0=0.3, delta=0.3, M=12, seed=23, dg=0,
+                    compat=False) as cb:
+        cb.set_state(q0)
+        cb.run(100, draws=False, nevals=False)
+        q = cb.get_state()
+    assert np.mean(np.abs(q[:, 0] - q0[:, 0]) > 1e-3) > 0.99          # the chains really moved
+    w = q[:, 0]
+    _check_moments(w, 0.0, 9.0)
+    z = q[:, 1] * np.exp(-0.5 * w)
+    _check_moments(z, 0.0, 1.0)

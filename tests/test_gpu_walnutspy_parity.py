@@ -299,3 +299,36 @@ def test_c2_100_transitions_vs_c_oracle(cuda_lib, integrator):
         assert ok, f"chain {c}: max rel err {err:.3e}"
         assert np.array_equal(out["diag"][:, c][:, EXACT_COLS], dg[:, EXACT_COLS])
         assert int(out["nevalF"][c] + out["nevalB"][c]) == ne
+
+
+@pytest.mark.parametrize("integrator", ["D", "R2P"])
+def test_compat_false_fixes_quirk_A14i(cuda_lib, integrator):
+    """compat=False adds the log-weight of the second backward leaf (reference defect A14(i)); parity against
+    the oracle run with the same correction, per transition on identical inputs (funnel), and the corrected
+    chain really differs from the compat one."""
+    from walnuts_b200 import ChainBatch
+    from oracle import c_oracle
+    rng = np.random.default_rng(3)
+    n, n_iter = 5, 60
+    q0 = np.empty((n, 11))
+    q0[:, 0] = rng.standard_normal(n)
+    q0[:, 1:] = np.exp(0.5 * q0[:, :1]) * rng.standard_normal((n, 10))
+    differs = False
+    with ChainBatch("funnel", 11, n, integrator=integrator, H0=0.3, delta=0.3, M=10, seed=99, compat=False) as cb:
+        for c in range(n):
+            dr, dg, _ = c_oracle.run_chain("funnel", integrator, q0[c], 0.3, 0.3, 10, n_iter, 99, c, compat=False)
+            dr_compat, _, _ = c_oracle.run_chain("funnel", integrator, q0[c], 0.3, 0.3, 10, n_iter, 99, c, compat=True)
+            differs = differs or not np.array_equal(dr, dr_compat)
+            if c == 0:
+                ref = np.empty((n_iter, n, 11))
+                refd = np.empty((n_iter, n, 24))
+            ref[:, c], refd[:, c] = dr, dg
+        prev = q0
+        for it in range(n_iter):
+            cb.set_state(prev)
+            out = cb.run(1, draws=True, diag=True)
+            ok, err = close(out["draws"][0], ref[it])
+            assert ok, f"transition {it}: {err:.3e}"
+            assert np.array_equal(out["diag"][0][:, EXACT_COLS], refd[it][:, EXACT_COLS])
+            prev = ref[it]
+    assert differs

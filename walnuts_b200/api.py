@@ -23,12 +23,16 @@ def _seed_from_global():
 def WALNUTS(lpFun, q0, generated=None, integrator=_ig.fixedLeapFrog, H0=0.2, stepSizeRandScale=0.2,
             delta0=0.05, numIter=2000, warmupIter=1000, M=10, igrAux=None, adaptH=True,
             adaptHtarget=0.8, adaptDelta=True, adaptDeltaTarget=0.6, adaptDeltaQuantile=0.9,
-            recordOrbitStats=False, *, seed=None, device=0, chain_offset=0):
+            recordOrbitStats=False, *, seed=None, device=0, chain_offset=0, compat=True):
     """Many-chain WALNUTS/NUTS with the WALNUTSpy driver semantics (WALNUTS.py:111-129 arguments).
 
     Returns (samples, diagnostics): for a single chain (`q0.ndim == 1`) shapes are (dg, numIter+1) and
     (numIter, 24) exactly as WALNUTS.py:163,180,724-727; with q0 of shape (n_chains, d) a leading
     chains axis is added.
+
+    `compat=True` (default) reproduces the reference bit-for-bit, including its defect A14(i): the second leaf
+    of a BACKWARD pair never adds its log-weight to the running sum (WALNUTS.py:420 has no counterpart after
+    :443-459), which measurably biases adaptive runs on the funnel.  `compat=False` adds it.
     """
     if adaptH and (adaptHtarget < 0.0 or adaptHtarget > 1.0):
         raise ValueError("bad adaptHtarget")          # sys.exit in the reference, WALNUTS.py:140
@@ -50,7 +54,7 @@ def WALNUTS(lpFun, q0, generated=None, integrator=_ig.fixedLeapFrog, H0=0.2, ste
     with ChainBatch(name, d, n_chains, mode="walnutspy", integrator=integrator.kind, H0=H0,
                     jitter=stepSizeRandScale, delta=delta0, M=M, minC=aux.minC, maxC=aux.maxC,
                     r2p_prob0=aux.R2Pprob0, seed=seed, chain_offset=chain_offset, device=device,
-                    data=data) as cb:
+                    compat=compat, data=data) as cb:
         if warmupIter > 0 and (adaptH or adaptDelta):
             cb.set_adapt(min(warmupIter, numIter), adaptH, adaptHtarget, adaptDelta, adaptDeltaTarget,
                          adaptDeltaQuantile)

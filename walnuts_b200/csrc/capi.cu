@@ -478,6 +478,7 @@ static int run_async_impl(wn_handle* h, int64_t n_iter, double* d_draws, double*
     memset(&P, 0, sizeof(P));
     P.n_chains = c.n_chains; P.d = c.d; P.dg = c.dg; P.M = c.M; P.kind = c.integrator;
     P.minC = c.minC; P.maxC = c.maxC; P.n_iter = (int)n_iter; P.iter0 = h->iter_done + 1;
+    P.compat = c.compat;
     P.seed_lo = (uint32_t)(c.seed & 0xffffffffu); P.seed_hi = (uint32_t)(c.seed >> 32);
     P.chain_offset = (uint32_t)c.chain_offset;
     P.H0 = c.H0; P.delta0 = c.delta; P.jitter = c.jitter; P.p0 = c.r2p_prob0;

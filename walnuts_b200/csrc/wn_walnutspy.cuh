@@ -25,6 +25,7 @@ namespace wn {
 struct RunParams {
   int n_chains, d, dg, M, kind, minC, maxC;
   int n_iter;
+  int compat;           // 1: reproduce reference quirk A14(i) (WALNUTS.py:420 has no counterpart after :443-459)
   uint32_t iter0;       // iteration number of the first transition of this call (1-based)
   uint32_t seed_lo, seed_hi;
   uint32_t chain_offset;
@@ -782,7 +783,7 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
           }
           double ls = side ? C.lwtSum1 : C.lwtSum0;
           if (level == 0) ls = lwt;                                                  // :321,354
-          else if (!(side == 1 && !(nleaf & 1u))) ls += lwt;                         // :420,507,550; quirk A14(i)
+          else if (!P.compat || !(side == 1 && !(nleaf & 1u))) ls += lwt;            // :420,507,550; quirk A14(i)
           if (side) C.lwtSum1 = ls; else C.lwtSum0 = ls;
           const double Wnew = exp(-Hfwd + C.H0 + ls);                                // :322,...
           bool pick;
