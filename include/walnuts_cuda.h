@@ -57,6 +57,7 @@ extern "C" {
 #define WN_INT_FIXED 0 /* adaptiveIntegrators.fixedLeapFrog     :49-59   (plain NUTS)        */
 #define WN_INT_D 1     /* adaptiveIntegrators.adaptLeapFrogD    :65-137                      */
 #define WN_INT_R2P 2   /* adaptiveIntegrators.adaptLeapFrogR2P  :361-475                     */
+#define WN_INT_YOSHIDA 3 /* adaptiveIntegrators.adaptYoshidaD   :142-240 (4th-order triple)  */
 
 #define WN_DIAG_COLS 24 /* WALNUTS.py:180,670-693 */
 

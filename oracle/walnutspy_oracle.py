@@ -23,7 +23,9 @@ import numpy as np
 LOG_ZERO = -700.0                       # constants.py:13
 WT_SUM_THRESH = float(np.exp(LOG_ZERO + 1.0))   # constants.py:14
 
-FIXED, ADAPT_D, ADAPT_R2P = 0, 1, 2
+FIXED, ADAPT_D, ADAPT_R2P, ADAPT_YOSHIDA = 0, 1, 2, 3
+Y_FIRSTLAST = 1.351207191959658       # adaptiveIntegrators.py:143-144
+Y_MIDDLE = -1.702414383919315
 
 
 class AuxPar:
@@ -45,9 +47,10 @@ def stop_condition(qm, vm, qp, vp):
     return bool(_pysum(vp * tmp) < 0.0 or _pysum(vm * tmp) < 0.0)
 
 
-def _pass(q, vv, g, h, c, lpFun, track):
-    """2**c leapfrog micro-steps of total length h (adaptiveIntegrators.py:70-84).
-    Returns (q, vv, g, f, H_last, all_finite, max|diff H|)."""
+def _pass(q, vv, g, h, c, lpFun, track, yoshida=False):
+    """2**c leapfrog micro-steps of total length h (adaptiveIntegrators.py:70-84); with `yoshida` each
+    micro-step is the 4th-order triple of leapfrogs of adaptYoshidaD (:156-175).
+    Returns (q, vv, g, f, H_last, all_finite, max|diff H|, hh, n_evals)."""
     nstep = 2 ** c
     hh = h / nstep
     Hprev = track
@@ -55,10 +58,17 @@ def _pass(q, vv, g, h, c, lpFun, track):
     maxd = 0.0
     f = None
     for _ in range(nstep):
-        vh = vv + 0.5 * hh * g
-        q = q + hh * vh
-        f, g = lpFun(q)
-        vv = vh + 0.5 * hh * g
+        if yoshida:
+            for cf in (Y_FIRSTLAST, Y_MIDDLE, Y_FIRSTLAST):
+                vh = vv + 0.5 * cf * hh * g
+                q = q + cf * hh * vh
+                f, g = lpFun(q)
+                vv = vh + 0.5 * cf * hh * g
+        else:
+            vh = vv + 0.5 * hh * g
+            q = q + hh * vh
+            f, g = lpFun(q)
+            vv = vh + 0.5 * hh * g
         Hk = -f + 0.5 * _pysum(vv * vv)
         ok = ok and bool(np.isfinite(Hk))
         dd = abs(Hk - Hprev)
@@ -82,11 +92,13 @@ def macro_step(kind, q, v, g, Ham0, h, xi, lpFun, delta, aux, rng):
         return dict(q=qq, v=xi * vv, grad=gn, H=H1, nF=1, nB=0, If=0, Ib=0, c=0, lwt=0.0, igrConst=igr)
 
     minC, maxC = aux.minC, aux.maxC
+    yo = kind == ADAPT_YOSHIDA                      # adaptYoshidaD :142-240 = adaptLeapFrogD with Yoshida steps
+    ev = 3 if yo else 1
     nF = 0
     If = maxC
     for c in range(minC, maxC + 1):                 # :69-94 / :365-389
-        qq, vv, gg, f, Hl, ok, maxd, hh = _pass(q, vv0, g, h, c, lpFun, Ham0)
-        nF += 2 ** c
+        qq, vv, gg, f, Hl, ok, maxd, hh = _pass(q, vv0, g, h, c, lpFun, Ham0, yo)
+        nF += ev * 2 ** c
         if ok and abs(Ham0 - Hl) < delta:
             If = c
             break
@@ -104,19 +116,19 @@ def macro_step(kind, q, v, g, Ham0, h, xi, lpFun, delta, aux, rng):
     with np.errstate(all="ignore"):
         igr = hh * (maxd ** (-1.0 / 3.0)) if maxd > 0 else np.inf   # :101,399,424
 
-    if kind == ADAPT_D or cSim == If:               # :104-132 / :430-433
+    if kind in (ADAPT_D, ADAPT_YOSHIDA) or cSim == If:   # :104-132 / :430-433
         maxTry, Ib = If - 1, If
     else:                                           # :434-437
         maxTry, Ib = maxC, maxC
     nB = 0
     for c in range(minC, maxTry + 1):               # :111-132 / :444-464
-        _, _, _, _, Hb, okb, _, _ = _pass(qO, -vO, gO, h, c, lpFun, HO)
-        nB += 2 ** c
+        _, _, _, _, Hb, okb, _, _ = _pass(qO, -vO, gO, h, c, lpFun, HO, yo)
+        nB += ev * 2 ** c
         if okb and abs(HO - Hb) < delta:
             Ib = c
             break
-    if kind == ADAPT_D:
-        lwt = (If != Ib) * LOG_ZERO                 # :136
+    if kind in (ADAPT_D, ADAPT_YOSHIDA):
+        lwt = (If != Ib) * LOG_ZERO                 # :136, :239
     else:                                           # :467-475
         lwtb = LOG_ZERO
         if cSim == Ib:

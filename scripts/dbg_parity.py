@@ -1,17 +1,15 @@
 import sys, numpy as np
 sys.path.insert(0, ".")
-from tests.helpers import oracle_walnutspy
-from tests.test_gpu_walnutspy_parity import run_cuda, sw_q0, FLOAT_COLS
+import walnuts_b200 as wb
 from oracle import targets as ot
-y = ot.load_sw_data()[:37]
-q0 = sw_q0(4, 37)
-out, st = run_cuda("stock_watson", q0, "R2P", 0.1, 0.3, 6, 6, 1234, 1, 10, {"y": y})
-dr, dg = oracle_walnutspy("stock_watson", q0, "R2P", 0.1, 0.3, 6, 6, 1234, [0,1,2,3], 1, 10, {"y": y})
-g = out["diag"]
-np.set_printoptions(linewidth=250, precision=12)
-err = np.abs(g - dg) / np.maximum(1, np.abs(dg))
-print("max err per col", err.max(axis=(0, 1)))
-i = np.unravel_index(np.argmax(err), err.shape); print(i, g[i], dg[i])
-print("draw err", np.max(np.abs(out["draws"] - dr) / np.maximum(1, np.abs(dr)), axis=(1, 2)))
-lp = ot.make_stock_watson(y)
-print("H scale", lp(q0[0])[0])
+from oracle import walnutspy_oracle as wo
+q0 = 0.5 * np.random.default_rng(2).standard_normal((3, 6))
+s, d = wb.WALNUTS(wb.targets.stdGauss, q0, integrator=wb.adaptYoshidaD, numIter=30, warmupIter=30, M=8, seed=3)
+np.set_printoptions(linewidth=220, precision=10)
+for c in range(1):
+    so, do = wo.WALNUTS(ot.std_normal, q0[c], integrator=wo.ADAPT_YOSHIDA, numIter=30, warmupIter=30, M=8, seed=3, chain=c, adaptH=True, adaptDelta=True)
+    err = np.max(np.abs(s[c] - so), axis=0)
+    print("draw err per iter", err[:20])
+    print("H cuda", d[c][:16, 15]); print("H orcl", do[:16, 15])
+    print("delta cuda", d[c][:16, 18]); print("delta orcl", do[:16, 18])
+    print("nF", d[c][:12, 6], do[:12, 6])

@@ -9,10 +9,10 @@ with `lpFun` / `logp` taken from the CUDA target registry in `walnuts_b200.targe
 from ._ffi import WalnutsError  # noqa: F401
 from .sampler import ChainBatch, fp64_peak  # noqa: F401
 from . import targets, integrators  # noqa: F401
-from .integrators import (fixedLeapFrog, adaptLeapFrogD, adaptLeapFrogR2P,  # noqa: F401
+from .integrators import (fixedLeapFrog, adaptLeapFrogD, adaptLeapFrogR2P, adaptYoshidaD,  # noqa: F401
                           integratorAuxPar)
 from .api import WALNUTS, walnuts, walnuts_step  # noqa: F401
 
 __all__ = ["ChainBatch", "WALNUTS", "walnuts", "walnuts_step", "targets", "integrators",
-           "fixedLeapFrog", "adaptLeapFrogD", "adaptLeapFrogR2P", "integratorAuxPar",
+           "fixedLeapFrog", "adaptLeapFrogD", "adaptLeapFrogR2P", "adaptYoshidaD", "integratorAuxPar",
            "WalnutsError", "fp64_peak"]

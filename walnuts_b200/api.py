@@ -42,7 +42,8 @@ def WALNUTS(lpFun, q0, generated=None, integrator=_ig.fixedLeapFrog, H0=0.2, ste
         raise NotImplementedError("recordOrbitStats with a custom `generated` is not available on the GPU: the "
                                   "orbit statistics are kept for the coordinates themselves (generated=None)")
     if not isinstance(integrator, _ig._Integrator):
-        raise TypeError("integrator must be one of walnuts_b200.fixedLeapFrog / adaptLeapFrogD / adaptLeapFrogR2P")
+        raise TypeError("integrator must be one of walnuts_b200.fixedLeapFrog / adaptLeapFrogD / adaptLeapFrogR2P / "
+                        "adaptYoshidaD")
     aux = igrAux or _ig.integratorAuxPar()
     q0 = np.asarray(q0, dtype=np.float64)
     single = q0.ndim == 1

@@ -161,7 +161,7 @@ static bool pick_plan(const wn_config& c, bool adapt, LaunchPlan& p) {
       // block-cooperative gradient (8 chains per CTA share every load of X) for the plain WALNUTSpy kernel;
       // the per-warp version serves package mode / warm-up adaptation and WN_VARIANT=1 (comparison)
       const char* v = getenv("WN_VARIANT");
-      if (pkg == 0 && !(v && atoi(v) == 1)) p = plan_wpy<LogRegCoopT, 32, 2, 256>();
+      if (pkg == 0 && c.integrator != WN_INT_YOSHIDA && !(v && atoi(v) == 1)) p = plan_wpy<LogRegCoopT, 32, 2, 256>();
       else p = plan_for<LogRegT, 32, 2, 256>(pkg);
       return true;
     }
@@ -259,7 +259,7 @@ int wn_create(const wn_config* cfg, wn_handle** out) {
   if (!(c.delta > 0)) return fail(h, WN_EINVAL, "non-positive max_error");
   if (c.mode != WN_MODE_WALNUTSPY && c.mode != WN_MODE_PACKAGE) return fail(h, WN_EINVAL, "bad mode");
   if (c.mode == WN_MODE_WALNUTSPY) {
-    if (c.integrator < WN_INT_FIXED || c.integrator > WN_INT_R2P) return fail(h, WN_EINVAL, "bad integrator");
+    if (c.integrator < WN_INT_FIXED || c.integrator > WN_INT_YOSHIDA) return fail(h, WN_EINVAL, "bad integrator");
     if (c.minC < 0 || c.maxC < c.minC || c.maxC > 30) return fail(h, WN_EINVAL, "need 0 <= minC <= maxC <= 30");
     if (!(c.jitter >= 0 && c.jitter < 1)) return fail(h, WN_EINVAL, "stepSizeRandScale must be in [0,1)");
   }

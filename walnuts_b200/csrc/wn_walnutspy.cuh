@@ -52,7 +52,9 @@ struct RunParams {
 };
 #define WN_ADAPT_STRIDE 16
 
-enum { KIND_FIXED = 0, KIND_D = 1, KIND_R2P = 2 };
+enum { KIND_FIXED = 0, KIND_D = 1, KIND_R2P = 2, KIND_YOSHIDA = 3 };   // 3: adaptYoshidaD (adaptiveIntegrators.py:142-240)
+#define WN_Y_FIRSTLAST 1.351207191959658
+#define WN_Y_MIDDLE (-1.702414383919315)
 enum { PH_FWD = 0, PH_REDO = 1, PH_BWD = 2, PH_INIT = 3 };
 enum { ST_CHAIN = 0, ST_ITER, ST_ITER2, ST_LEVEL, ST_MACRO, ST_PASS_END, ST_LEAF, ST_LEVEL_END, ST_ITER_END, ST_RUN, ST_EXIT };
 
@@ -131,6 +133,10 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
   bool rsearch = false, rexact = false, rlazyok = false;
   double rh = 0, rHref = 0, rdelta = 0, rsign = 1.0;
   unsigned long long rEv = 0;
+  const bool yoshida = (P.kind == KIND_YOSHIDA);
+  const unsigned long long evmul = yoshida ? 3ull : 1ull;   // gradient evaluations per micro-step
+  int ysub = 0;            // Yoshida: index of the next leapfrog inside the triple
+  double hh0 = 0;          // Yoshida: the micro-step size the triple is built from
   // ADAPT: per-step energies of the forward passes (igrConst, adaptiveIntegrators.py:101,399,424)
   bool trackH = false;
   double hist[4];
@@ -251,14 +257,16 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
     }
   };
   auto start_pass = [&](int cc) {
-    steps_left = 1u << cc;
+    steps_left = (yoshida ? 3u : 1u) << cc;
     hh = ldexp(rh, -cc);
     ha = 0.5 * hh;
+    hh0 = hh;
+    ysub = 0;
     expmax = 0;
     smax = 0;
     umax = 0;
     if constexpr (Target::LAZY_ENERGY) {
-      lazy = rlazyok && !rexact && (cc >= 2) && !trackH;
+      lazy = rlazyok && !rexact && (cc >= 2) && !trackH && !yoshida;
       if (lazy) {
         track_state();   // the pass starts from a bounded state
         since = 0;
@@ -370,7 +378,27 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
         st = ST_PASS_END;
       }
     } else if (st == ST_RUN) {
-      if (ADAPT && trackH) {   // warm-up: every step's energy is needed for igrConst
+      if (yoshida) {
+        // one leapfrog of the 4th-order triple (coefficients firstLast, middle, firstLast, :157-173); the
+        // energy (Hams[i], :175) and its finiteness only count after the third
+        const double cf = (ysub == 1) ? WN_Y_MIDDLE : WN_Y_FIRSTLAST;
+        hh = __dmul_rn(cf, hh0);
+        ha = __dmul_rn(__dmul_rn(0.5, cf), hh0);
+        const int em = expmax;
+        micro_step();
+        const bool full = (ysub == 2);
+        if (!full) expmax = em;
+        ysub = full ? 0 : ysub + 1;
+        --steps_left;
+        if constexpr (ADAPT) {
+          if (trackH && full) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) hist[i] = (nh == i) ? hp : hist[i];
+            ++nh;
+          }
+          if (trackH && (nh == 4 || steps_left == 0u)) flush_hist();
+        }
+      } else if (ADAPT && trackH) {   // warm-up: every step's energy is needed for igrConst
         micro_step();
 #pragma unroll
         for (int i = 0; i < 4; ++i) hist[i] = (nh == i) ? hp : hist[i];
@@ -614,7 +642,7 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
             // fast path of the search (adaptiveIntegrators.py:69-94, 111-132): attempt failed -> next c
             const bool ok = !anybad && fabs(rHref - Hend) < rdelta;
             if (!ok && rc < rlim) {
-              rEv += 1ull << rc;
+              rEv += evmul << rc;
               ++rc;
               rexact = false;
               load_ck(rsign);
@@ -645,7 +673,7 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
           }
           rexact = false;
           if (phase == PH_FWD) {
-            C.nF = C.nF + (1ull << c);
+            C.nF = C.nF + (evmul << c);
             const bool ok = !anybad && fabs(C.Ham0 - Hend) < C.delta;   // adaptiveIntegrators.py:87-92
             if (!(P.kind == KIND_FIXED || ok || c == P.maxC)) {
               ++c;
@@ -673,7 +701,7 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
               }
             }
           } else if (phase == PH_REDO) {
-            C.nF = C.nF + (1ull << C.cSim);
+            C.nF = C.nF + (evmul << C.cSim);
             C.lwtf = P.log_1mp0;
           }
           if (phase != PH_BWD) {
@@ -686,7 +714,7 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
                   C.igr = rh * pow((ad > 1.0e-10) ? ad : 1.0e-10, -1.0 / 3.0);
                 } else {                         // :101,399,424 (last forward pass)
                   const double md = C.maxd;
-                  C.igr = (md > 0.0 || md != md) ? hh * pow(md, -1.0 / 3.0) : INFINITY;
+                  C.igr = (md > 0.0 || md != md) ? hh0 * pow(md, -1.0 / 3.0) : INFINITY;
                 }
               }
               trackH = false;
@@ -699,7 +727,7 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
             }
             const int If = C.If, cSim = C.cSim;
             int maxTry, Ib;
-            if (P.kind == KIND_D || cSim == If) { maxTry = If - 1; Ib = If; }   // :104-111 / :430-433
+            if (P.kind != KIND_R2P || cSim == If) { maxTry = If - 1; Ib = If; }   // :104-111 / :195-202 / :430-433
             else { maxTry = P.maxC; Ib = P.maxC; }                              // :434-437
             C.maxTry = maxTry;
             C.Ib = Ib;
@@ -717,7 +745,7 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
               break;
             }
           } else {
-            C.nB = C.nB + (1ull << c);
+            C.nB = C.nB + (evmul << c);
             const bool ok = !anybad && fabs(C.Hfwd - Hend) < C.delta;   // :129-132 / :461-464
             if (ok) C.Ib = c;
             if (!ok && c < C.maxTry) {
@@ -733,8 +761,8 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
           // macro step complete
           {
             const int If = C.If, Ib = C.Ib, cSim = C.cSim;
-            if (P.kind == KIND_D) {
-              C.lwt = (If != Ib) ? WN_LOG_ZERO : 0.0;                  // :136
+            if (P.kind != KIND_R2P) {
+              C.lwt = (If != Ib) ? WN_LOG_ZERO : 0.0;                  // :136, :239
             } else {
               double lwtb = WN_LOG_ZERO;                               // :467-471
               if (cSim == Ib) lwtb = P.log_p0;

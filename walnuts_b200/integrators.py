@@ -21,6 +21,7 @@ class _Integrator:
 fixedLeapFrog = _Integrator("fixedLeapFrog", 0, "adaptiveIntegrators.py:49-59")
 adaptLeapFrogD = _Integrator("adaptLeapFrogD", 1, "adaptiveIntegrators.py:65-137")
 adaptLeapFrogR2P = _Integrator("adaptLeapFrogR2P", 2, "adaptiveIntegrators.py:361-475")
+adaptYoshidaD = _Integrator("adaptYoshidaD", 3, "adaptiveIntegrators.py:142-240")
 
 
 class integratorAuxPar:

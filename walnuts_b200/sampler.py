@@ -37,7 +37,7 @@ class ChainBatch:
         cfg = _ffi.WnConfig()
         cfg.target = _ffi.TARGETS[target] if isinstance(target, str) else int(target)
         cfg.mode = {"walnutspy": _ffi.MODE_WALNUTSPY, "package": _ffi.MODE_PACKAGE}[mode]
-        cfg.integrator = {"fixed": 0, "D": 1, "R2P": 2}[integrator] if isinstance(integrator, str) else int(integrator)
+        cfg.integrator = {"fixed": 0, "D": 1, "R2P": 2, "Yoshida": 3}[integrator] if isinstance(integrator, str) else int(integrator)
         cfg.d, cfg.n_chains, cfg.device = int(d), int(n_chains), int(device)
         cfg.dg = int(d if dg is None else dg)
         cfg.M, cfg.minC, cfg.maxC = int(M), int(minC), int(maxC)
