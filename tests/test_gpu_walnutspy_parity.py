@@ -367,3 +367,30 @@ def test_yoshida_with_default_adaptation(cuda_lib):
         ok, err = close(d[c][:, [15, 18]], do[:, [15, 18]], rtol=1e-6)
         assert ok, err
         assert np.array_equal(d[c][:, [1, 6, 7, 19]], do[:, [1, 6, 7, 19]])
+
+
+@pytest.mark.parametrize("case", range(14))
+def test_randomised_configurations(cuda_lib, case):
+    """Seeded sweep over dimensions (every kernel instantiation: G = 1, 4, 16, 32, 128/64, 256), integrators and
+    tuning parameters, diag-Gaussian targets with random scales; oracle = C restatement (pinned to the goldens)."""
+    from oracle import c_oracle
+    rng = np.random.default_rng(1000 + case)
+    d = int([1, 2, 4, 5, 12, 13, 31, 32, 33, 128, 129, 512, 513, 2048][case])
+    integ = ["fixed", "D", "R2P"][case % 3]
+    M = int(rng.integers(3, 9))
+    minC = int(rng.integers(0, 3))
+    maxC = minC + int(rng.integers(0, 6))
+    delta = float(rng.choice([0.05, 0.3, 1.0]))
+    sigma = np.exp(rng.uniform(-1.0, 1.0, d))
+    H0 = float(rng.uniform(0.2, 1.2)) * sigma.min() * (1.0 if integ != "fixed" else 0.5) * d ** -0.25 * 2.0
+    n_chains, n_iter = 5, 25
+    q0 = rng.standard_normal((n_chains, d)) * sigma
+    seed = int(rng.integers(1, 2 ** 40))
+    inv_var = 1.0 / sigma ** 2
+    out, state = run_cuda("diag_gauss", q0, integ, H0, delta, M, n_iter, seed, minC, maxC, {"inv_var": inv_var})
+    for c in (0, n_chains - 1):
+        dr, dg, ne = c_oracle.run_chain("diag_gauss", integ, q0[c], H0, delta, M, n_iter, seed, c, minC, maxC, inv_var=inv_var)
+        ok, err = close(out["draws"][:, c], dr)
+        assert ok, f"d={d} {integ}: max rel err {err:.3e}"
+        assert np.array_equal(out["diag"][:, c][:, EXACT_COLS], dg[:, EXACT_COLS]), f"d={d} {integ}"
+        assert int(out["nevalF"][c] + out["nevalB"][c]) == ne
