@@ -216,298 +216,292 @@ __global__ void __launch_bounds__(NT, MINB) package_kernel(const __grid_constant
       st = PS_PASS_END;
     }
     // =============================== cold state machine ==========================================
-    while (st != PS_RUN && st != PS_EXIT) {
-      switch (st) {
-        case PS_CHAIN: {
-          uint32_t cidx = 0;
-          if (t == 0) cidx = atomicAdd(P.queue, 1u);
-          cidx = Grp::bcast0(cidx, &sh_bcast);
-          if (cidx >= (uint32_t)P.n_chains) {
-            st = PS_EXIT;
-            break;
-          }
-          C.chain = P.chain_offset + cidx;
-#pragma unroll
-          for (int e = 0; e < E; ++e) {
-            const int j = target.coord(e, t);
-            q[e] = (j < P.d) ? P.state[(size_t)cidx * P.d + j] : 0.0;
-          }
-          C.it = 0;
-          C.chainEv = 0;
-          st = PS_ITER;
-          break;
-        }
-        case PS_ITER: {  // walnuts_step :322-327
-          RngKey key{P.seed_lo, P.seed_hi, C.chain, P.iter0 + (uint32_t)C.it};
-          C.iter = key.iter;
-          double x[2];
-          {
-            double ke = 0.0;
-#pragma unroll
-            for (int e = 0; e < E; ++e) {   // rho = inv_mass**-0.5 * N(0, I), :322-325
-              const int j = target.coord(e, t);
-              double z0 = 0.0, z1 = 0.0;
-              if (j < P.d) rng_normal_pair(key, STREAM_MOM, (uint32_t)(j >> 1), z0, z1);
-              v[e] = (j < P.d) ? __dmul_rn(pow(im[e], -0.5), (j & 1) ? z1 : z0) : 0.0;
-              ke = fma(im[e] * v[e], v[e], ke);
-            }
-            x[0] = target.lp_grad(q, g, red, parity);
-            x[1] = ke;
-          }
-          C.nev = 1;
-          Grp::template sum<2>(x, red, parity);
-          const double w0 = -(-x[0] + 0.5 * x[1]);          // -H(theta, rho), :326
-          C.lpO = x[0];
-          C.keO = x[1];
-          C.lpP = x[0];
-          C.keP = x[1];
-          C.wL = w0;
-          C.wR = w0;
-          C.lse_old = w0;
-#pragma unroll
-          for (int e2 = 0; e2 < E2; ++e2) {
-            const double2 qq = make_double2(q[2 * e2], q[2 * e2 + 1]);
-            *sc(V_PARK_Q, e2) = qq;
-            *sc(V_PARK_V, e2) = make_double2(v[2 * e2], v[2 * e2 + 1]);
-            *sc(V_PARK_G, e2) = make_double2(g[2 * e2], g[2 * e2 + 1]);
-            *sc(V_PROP0, e2) = qq;
-          }
-          C.propCur = 0;
-          C.back = -1;
-          C.depth = 0;
-          st = PS_DEPTH;
-          break;
-        }
-        case PS_DEPTH: {  // :328-342 start of an extension
-          const int depth = C.depth, prev = C.back;
-          const int back = (keyed(STREAM_PKG_DIR, (uint32_t)depth) >= 0.5) ? 1 : 0;   // :330
-          // registers hold the end of side `prev` with its STORED momentum; the other end is parked
-          if (prev >= 0 && back != prev) {
-#pragma unroll
-            for (int e2 = 0; e2 < E2; ++e2) {
-              const double2 pq = *sc(V_PARK_Q, e2), pv = *sc(V_PARK_V, e2), pg = *sc(V_PARK_G, e2);
-              *sc(V_PARK_Q, e2) = make_double2(q[2 * e2], q[2 * e2 + 1]);
-              *sc(V_PARK_V, e2) = make_double2(v[2 * e2], v[2 * e2 + 1]);
-              *sc(V_PARK_G, e2) = make_double2(g[2 * e2], g[2 * e2 + 1]);
-              q[2 * e2] = pq.x; q[2 * e2 + 1] = pq.y;
-              v[2 * e2] = pv.x; v[2 * e2 + 1] = pv.y;
-              g[2 * e2] = pg.x; g[2 * e2 + 1] = pg.y;
-            }
-            // log density / kinetic term of the two ends travel with them
-            const double lpo = C.lpO, keo = C.keO;
-            C.lpO = C.lpP;
-            C.keO = C.keP;
-            C.lpP = lpo;
-            C.keP = keo;
-          }
-          if (back) {   // rho = -rho (:245)
-#pragma unroll
-            for (int e = 0; e < E; ++e) v[e] = -v[e];
-          }
-          C.back = back;
-          C.weight = back ? C.wL : C.wR;      // :244,248
-          C.k = 0;
-          C.n_new = 1u << depth;
-          C.lse_ext = -INFINITY;
-          C.candValid = 0;
-          C.sub = 0;
-          st = PS_MACRO;
-          break;
-        }
-        case PS_MACRO: {  // one macro step of extend_orbit (:251-273): start the forward stable_steps search
-          C.k = C.k + 1u;
-          // registers: (theta, rho in integration convention, grad(theta)); lpO/keO are its lp and rho.M^-1.rho
-          const double lpS = C.lpO, keS = C.keO;
-          C.lpS = lpS;
-          C.keS = keS;
-          const double HS = -lpS + 0.5 * keS;
-          C.HS = HS;
-          C.p0 = -HS;                                  // :252
-          save_ck();                                   // S
-          C.phase = PK_STABLE_F;
-          C.n = 0;
-          C.Hmin = HS;                                 // :165
-          C.Hmax = HS;
-          start_pass(P.macro_step, 1u, true, false);
+    // handlers in transition order (every transition goes down this list): see wn_walnutspy.cuh
+    if (st == PS_PASS_END) do {
+      const int phase = C.phase;
+      if (phase != PK_LEAP) {
+        // stable_steps pass n finished (:161-182)
+        const int n = C.n;
+        C.nev = C.nev + (1ull << n);
+        const bool ok = (C.Hmax - C.Hmin) <= P.max_error;                    // :180
+        if (!ok && n < 10) {
+          C.n = n + 1;
+          load_ck(phase == PK_STABLE_F ? 1.0 : -1.0);
+          C.Hmin = C.HS;
+          C.Hmax = C.HS;
+          start_pass(ldexp(P.macro_step, -(n + 1)), 1u << (n + 1), true, false);
           st = PS_RUN;
           break;
         }
-        case PS_PASS_END: {
-          const int phase = C.phase;
-          if (phase != PK_LEAP) {
-            // stable_steps pass n finished (:161-182)
-            const int n = C.n;
-            C.nev = C.nev + (1ull << n);
-            const bool ok = (C.Hmax - C.Hmin) <= P.max_error;                    // :180
-            if (!ok && n < 10) {
-              C.n = n + 1;
-              load_ck(phase == PK_STABLE_F ? 1.0 : -1.0);
-              C.Hmin = C.HS;
-              C.Hmax = C.HS;
-              start_pass(ldexp(P.macro_step, -(n + 1)), 1u << (n + 1), true, false);
-              st = PS_RUN;
-              break;
-            }
-            const int es = 1 << n;                                               // :181-182
-            if (phase == PK_STABLE_F) {
-              C.ell_s = es;
-              const double u = keyed(STREAM_PKG_ELL, C.n_new - 1u + C.k - 1u);   // :194,256
-              int lo = es / 2;
-              if (!P.compat && lo < 1) lo = 1;
-              const int pickI = min(2, (int)floor(3.0 * u));
-              const int ell = (pickI == 0) ? lo : (pickI == 1 ? es : 2 * es);
-              C.ell = ell;
-              load_ck(1.0);
-              C.phase = PK_LEAP;
-              // ell == 0 (defect B3): macro_step / 0 = inf and range(-1) is empty: one step of size inf
-              const double stp = (ell > 0) ? P.macro_step / (double)ell : INFINITY;   // :259
-              start_pass(stp, ell > 0 ? (uint32_t)ell : 1u, false, true);
-              st = PS_RUN;
-              break;
-            }
-            // backward search done: ell_stable_next known; restore O and finish the macro step
-            C.ell_n = es;
-            load_ck(1.0);
-            st = PS_LEAF;
-            break;
-          }
-          // leapfrog (:258) finished: registers hold O = (theta', rho', grad')
-          {
-            const int ell = C.ell;
-            C.nev = C.nev + (unsigned long long)(ell > 0 ? ell : 1);
-            double x[2] = {lpp, 0.0};
-#pragma unroll
-            for (int e = 0; e < E; ++e) x[1] = fma(im[e] * v[e], v[e], x[1]);
-            Grp::template sum<2>(x, red, parity);
-            C.lpO = x[0];
-            C.keO = x[1];
-            const double HO = -x[0] + 0.5 * x[1];
-            save_ck();                                  // O replaces S
-            C.phase = PK_STABLE_B;                      // stable_steps(theta, -rho) (:261)
-            C.n = 0;
-            C.HS = HO;
-            C.Hmin = HO;
-            C.Hmax = HO;
-#pragma unroll
-            for (int e = 0; e < E; ++e) v[e] = -v[e];
-            start_pass(P.macro_step, 1u, true, false);
-            st = PS_RUN;
-          }
+        const int es = 1 << n;                                               // :181-182
+        if (phase == PK_STABLE_F) {
+          C.ell_s = es;
+          const double u = keyed(STREAM_PKG_ELL, C.n_new - 1u + C.k - 1u);   // :194,256
+          int lo = es / 2;
+          if (!P.compat && lo < 1) lo = 1;
+          const int pickI = min(2, (int)floor(3.0 * u));
+          const int ell = (pickI == 0) ? lo : (pickI == 1 ? es : 2 * es);
+          C.ell = ell;
+          load_ck(1.0);
+          C.phase = PK_LEAP;
+          // ell == 0 (defect B3): macro_step / 0 = inf and range(-1) is empty: one step of size inf
+          const double stp = (ell > 0) ? P.macro_step / (double)ell : INFINITY;   // :259
+          start_pass(stp, ell > 0 ? (uint32_t)ell : 1u, false, true);
+          st = PS_RUN;
           break;
         }
-        case PS_LEAF: {  // weight update, online pick, sub-U-turn checks (:264-273, :343, :349-350)
-          const int depth = C.depth, back = C.back, ell = C.ell;
-          const uint32_t k = C.k;
-          const double p1 = -(-C.lpO + 0.5 * C.keO);                                      // :264
-          double w = __dadd_rn(p1, -C.p0);
-          w = __dadd_rn(w, logp_ell(ell, C.ell_n));
-          w = __dadd_rn(w, -logp_ell(ell, C.ell_s));
-          w = __dadd_rn(w, C.weight);                                                      // :265-271
-          C.weight = w;
-          const double lse = logaddexp(C.lse_ext, w);
-          C.lse_ext = lse;
-          const double us = keyed(STREAM_PKG_SELECT, C.n_new - 1u + k - 1u);
-          if (lse > -INFINITY && us < exp(w - lse)) {
-            const int pv = V_PROP0 + (C.propCur ^ 1);
+        // backward search done: ell_stable_next known; restore O and finish the macro step
+        C.ell_n = es;
+        load_ck(1.0);
+        st = PS_LEAF;
+        break;
+      }
+      // leapfrog (:258) finished: registers hold O = (theta', rho', grad')
+      {
+        const int ell = C.ell;
+        C.nev = C.nev + (unsigned long long)(ell > 0 ? ell : 1);
+        double x[2] = {lpp, 0.0};
 #pragma unroll
-            for (int e2 = 0; e2 < E2; ++e2) *sc(pv, e2) = make_double2(q[2 * e2], q[2 * e2 + 1]);
-            C.candValid = 1;
-          }
-          // stored momentum: as integrated (reference, :272) or forward-time (compat == 0)
-          const double vs = (P.compat || !back) ? 1.0 : -1.0;
-          bool sub = false;
-          if (depth > 0) {
-            if (k & 1u) {
-              const int lvl = (k == 1u) ? depth : (__ffs(k - 1u) - 1);
+        for (int e = 0; e < E; ++e) x[1] = fma(im[e] * v[e], v[e], x[1]);
+        Grp::template sum<2>(x, red, parity);
+        C.lpO = x[0];
+        C.keO = x[1];
+        const double HO = -x[0] + 0.5 * x[1];
+        save_ck();                                  // O replaces S
+        C.phase = PK_STABLE_B;                      // stable_steps(theta, -rho) (:261)
+        C.n = 0;
+        C.HS = HO;
+        C.Hmin = HO;
+        C.Hmax = HO;
 #pragma unroll
-              for (int e2 = 0; e2 < E2; ++e2) {
-                *sc(V_STACK + 2 * lvl, e2) = make_double2(q[2 * e2], q[2 * e2 + 1]);
-                *sc(V_STACK + 2 * lvl + 1, e2) = make_double2(vs * v[2 * e2], vs * v[2 * e2 + 1]);
-              }
-            } else {
-              for (int s = 1; s <= depth && (k & ((1u << s) - 1u)) == 0u; ++s) {
-                const uint32_t m = k - (1u << s) + 1u;
-                const int lvl = (m == 1u) ? depth : (__ffs(m - 1u) - 1);
-                // list order after the [::-1] of :275: backward -> current state comes first
-                if (uturn_vs(V_STACK + 2 * lvl, V_STACK + 2 * lvl + 1, vs, back != 0)) {
-                  sub = true;
-                  break;
-                }
-              }
-            }
-          }
-          if (sub) {                     // :343-344
-            C.sub = 1;
-            st = PS_ITER_END;
-          } else {
-            st = (k == C.n_new) ? PS_DEPTH_END : PS_MACRO;
-          }
-          break;
-        }
-        case PS_DEPTH_END: {  // :345-358
-          const int depth = C.depth, back = C.back;
-          const double ua = keyed(STREAM_PKG_ACCEPT, (uint32_t)depth);
-          const double lse_ext = C.lse_ext, lse_old = C.lse_old;
-          if (log(ua) < lse_ext - lse_old) {                                       // :345-347
-            if (C.candValid) C.propCur = C.propCur ^ 1;                              // :349-350
-          }
-          C.candValid = 0;
-          // the new end is the last generated state with its stored momentum (:351)
-          const double vs = (P.compat || !back) ? 1.0 : -1.0;
+        for (int e = 0; e < E; ++e) v[e] = -v[e];
+        start_pass(P.macro_step, 1u, true, false);
+        st = PS_RUN;
+      }
+      break;
+    } while (0);
+    if (st == PS_LEAF) do {  // weight update, online pick, sub-U-turn checks (:264-273, :343, :349-350)
+      const int depth = C.depth, back = C.back, ell = C.ell;
+      const uint32_t k = C.k;
+      const double p1 = -(-C.lpO + 0.5 * C.keO);                                      // :264
+      double w = __dadd_rn(p1, -C.p0);
+      w = __dadd_rn(w, logp_ell(ell, C.ell_n));
+      w = __dadd_rn(w, -logp_ell(ell, C.ell_s));
+      w = __dadd_rn(w, C.weight);                                                      // :265-271
+      C.weight = w;
+      const double lse = logaddexp(C.lse_ext, w);
+      C.lse_ext = lse;
+      const double us = keyed(STREAM_PKG_SELECT, C.n_new - 1u + k - 1u);
+      if (lse > -INFINITY && us < exp(w - lse)) {
+        const int pv = V_PROP0 + (C.propCur ^ 1);
 #pragma unroll
-          for (int e = 0; e < E; ++e) v[e] = vs * v[e];
-          if (back) C.wL = C.weight; else C.wR = C.weight;
-          // uturn(orbit[0], orbit[-1]) (:352): left first
-          const bool joined = uturn_vs(V_PARK_Q, V_PARK_V, 1.0, back != 0);
-          if (joined || depth + 1 == P.max_depth) {
-            st = PS_ITER_END;
-            break;
-          }
-          C.lse_old = logaddexp(lse_old, lse_ext);                                 // :354-358
-          C.depth = depth + 1;
-          st = PS_DEPTH;
-          break;
-        }
-        case PS_ITER_END: {
-          const int pv = V_PROP0 + C.propCur;
+        for (int e2 = 0; e2 < E2; ++e2) *sc(pv, e2) = make_double2(q[2 * e2], q[2 * e2 + 1]);
+        C.candValid = 1;
+      }
+      // stored momentum: as integrated (reference, :272) or forward-time (compat == 0)
+      const double vs = (P.compat || !back) ? 1.0 : -1.0;
+      bool sub = false;
+      if (depth > 0) {
+        if (k & 1u) {
+          const int lvl = (k == 1u) ? depth : (__ffs(k - 1u) - 1);
 #pragma unroll
           for (int e2 = 0; e2 < E2; ++e2) {
-            const double2 qq = *sc(pv, e2);
-            q[2 * e2] = qq.x;
-            q[2 * e2 + 1] = qq.y;
+            *sc(V_STACK + 2 * lvl, e2) = make_double2(q[2 * e2], q[2 * e2 + 1]);
+            *sc(V_STACK + 2 * lvl + 1, e2) = make_double2(vs * v[2 * e2], vs * v[2 * e2 + 1]);
           }
-          const uint32_t cidx = C.chain - P.chain_offset;
-          const int it = C.it;
-          const size_t row = (size_t)it * P.n_chains + cidx;
-          if (P.draws) {
-#pragma unroll
-            for (int e = 0; e < E; ++e) {
-              const int j = target.coord(e, t);
-              if (j < P.dg) P.draws[row * P.dg + j] = q[e];
+        } else {
+          for (int s = 1; s <= depth && (k & ((1u << s) - 1u)) == 0u; ++s) {
+            const uint32_t m = k - (1u << s) + 1u;
+            const int lvl = (m == 1u) ? depth : (__ffs(m - 1u) - 1);
+            // list order after the [::-1] of :275: backward -> current state comes first
+            if (uturn_vs(V_STACK + 2 * lvl, V_STACK + 2 * lvl + 1, vs, back != 0)) {
+              sub = true;
+              break;
             }
           }
-          const unsigned long long ce = C.chainEv + C.nev;
-          C.chainEv = ce;
-          C.it = it + 1;
-          if (it + 1 < P.n_iter) {
-            st = PS_ITER;
-            break;
-          }
-#pragma unroll
-          for (int e = 0; e < E; ++e) {
-            const int j = target.coord(e, t);
-            if (j < P.d) P.state[(size_t)cidx * P.d + j] = q[e];
-          }
-          if (t == 0 && P.neval) P.neval[cidx] = ce;
-          tot += ce;
-          st = PS_CHAIN;
-          break;
         }
-        default:
-          st = PS_EXIT;
-          break;
       }
-    }
+      if (sub) {                     // :343-344
+        C.sub = 1;
+        st = PS_ITER_END;
+      } else {
+        st = (k == C.n_new) ? PS_DEPTH_END : PS_MACRO;
+      }
+      break;
+    } while (0);
+    if (st == PS_DEPTH_END) do {  // :345-358
+      const int depth = C.depth, back = C.back;
+      const double ua = keyed(STREAM_PKG_ACCEPT, (uint32_t)depth);
+      const double lse_ext = C.lse_ext, lse_old = C.lse_old;
+      if (log(ua) < lse_ext - lse_old) {                                       // :345-347
+        if (C.candValid) C.propCur = C.propCur ^ 1;                              // :349-350
+      }
+      C.candValid = 0;
+      // the new end is the last generated state with its stored momentum (:351)
+      const double vs = (P.compat || !back) ? 1.0 : -1.0;
+#pragma unroll
+      for (int e = 0; e < E; ++e) v[e] = vs * v[e];
+      if (back) C.wL = C.weight; else C.wR = C.weight;
+      // uturn(orbit[0], orbit[-1]) (:352): left first
+      const bool joined = uturn_vs(V_PARK_Q, V_PARK_V, 1.0, back != 0);
+      if (joined || depth + 1 == P.max_depth) {
+        st = PS_ITER_END;
+        break;
+      }
+      C.lse_old = logaddexp(lse_old, lse_ext);                                 // :354-358
+      C.depth = depth + 1;
+      st = PS_DEPTH;
+      break;
+    } while (0);
+    if (st == PS_ITER_END) do {
+      const int pv = V_PROP0 + C.propCur;
+#pragma unroll
+      for (int e2 = 0; e2 < E2; ++e2) {
+        const double2 qq = *sc(pv, e2);
+        q[2 * e2] = qq.x;
+        q[2 * e2 + 1] = qq.y;
+      }
+      const uint32_t cidx = C.chain - P.chain_offset;
+      const int it = C.it;
+      const size_t row = (size_t)it * P.n_chains + cidx;
+      if (P.draws) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          const int j = target.coord(e, t);
+          if (j < P.dg) P.draws[row * P.dg + j] = q[e];
+        }
+      }
+      const unsigned long long ce = C.chainEv + C.nev;
+      C.chainEv = ce;
+      C.it = it + 1;
+      if (it + 1 < P.n_iter) {
+        st = PS_ITER;
+        break;
+      }
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const int j = target.coord(e, t);
+        if (j < P.d) P.state[(size_t)cidx * P.d + j] = q[e];
+      }
+      if (t == 0 && P.neval) P.neval[cidx] = ce;
+      tot += ce;
+      st = PS_CHAIN;
+      break;
+    } while (0);
+    if (st == PS_CHAIN) do {
+      uint32_t cidx = 0;
+      if (t == 0) cidx = atomicAdd(P.queue, 1u);
+      cidx = Grp::bcast0(cidx, &sh_bcast);
+      if (cidx >= (uint32_t)P.n_chains) {
+        st = PS_EXIT;
+        break;
+      }
+      C.chain = P.chain_offset + cidx;
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const int j = target.coord(e, t);
+        q[e] = (j < P.d) ? P.state[(size_t)cidx * P.d + j] : 0.0;
+      }
+      C.it = 0;
+      C.chainEv = 0;
+      st = PS_ITER;
+      break;
+    } while (0);
+    if (st == PS_ITER) do {  // walnuts_step :322-327
+      RngKey key{P.seed_lo, P.seed_hi, C.chain, P.iter0 + (uint32_t)C.it};
+      C.iter = key.iter;
+      double x[2];
+      {
+        double ke = 0.0;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {   // rho = inv_mass**-0.5 * N(0, I), :322-325
+          const int j = target.coord(e, t);
+          double z0 = 0.0, z1 = 0.0;
+          if (j < P.d) rng_normal_pair(key, STREAM_MOM, (uint32_t)(j >> 1), z0, z1);
+          v[e] = (j < P.d) ? __dmul_rn(pow(im[e], -0.5), (j & 1) ? z1 : z0) : 0.0;
+          ke = fma(im[e] * v[e], v[e], ke);
+        }
+        x[0] = target.lp_grad(q, g, red, parity);
+        x[1] = ke;
+      }
+      C.nev = 1;
+      Grp::template sum<2>(x, red, parity);
+      const double w0 = -(-x[0] + 0.5 * x[1]);          // -H(theta, rho), :326
+      C.lpO = x[0];
+      C.keO = x[1];
+      C.lpP = x[0];
+      C.keP = x[1];
+      C.wL = w0;
+      C.wR = w0;
+      C.lse_old = w0;
+#pragma unroll
+      for (int e2 = 0; e2 < E2; ++e2) {
+        const double2 qq = make_double2(q[2 * e2], q[2 * e2 + 1]);
+        *sc(V_PARK_Q, e2) = qq;
+        *sc(V_PARK_V, e2) = make_double2(v[2 * e2], v[2 * e2 + 1]);
+        *sc(V_PARK_G, e2) = make_double2(g[2 * e2], g[2 * e2 + 1]);
+        *sc(V_PROP0, e2) = qq;
+      }
+      C.propCur = 0;
+      C.back = -1;
+      C.depth = 0;
+      st = PS_DEPTH;
+      break;
+    } while (0);
+    if (st == PS_DEPTH) do {  // :328-342 start of an extension
+      const int depth = C.depth, prev = C.back;
+      const int back = (keyed(STREAM_PKG_DIR, (uint32_t)depth) >= 0.5) ? 1 : 0;   // :330
+      // registers hold the end of side `prev` with its STORED momentum; the other end is parked
+      if (prev >= 0 && back != prev) {
+#pragma unroll
+        for (int e2 = 0; e2 < E2; ++e2) {
+          const double2 pq = *sc(V_PARK_Q, e2), pv = *sc(V_PARK_V, e2), pg = *sc(V_PARK_G, e2);
+          *sc(V_PARK_Q, e2) = make_double2(q[2 * e2], q[2 * e2 + 1]);
+          *sc(V_PARK_V, e2) = make_double2(v[2 * e2], v[2 * e2 + 1]);
+          *sc(V_PARK_G, e2) = make_double2(g[2 * e2], g[2 * e2 + 1]);
+          q[2 * e2] = pq.x; q[2 * e2 + 1] = pq.y;
+          v[2 * e2] = pv.x; v[2 * e2 + 1] = pv.y;
+          g[2 * e2] = pg.x; g[2 * e2 + 1] = pg.y;
+        }
+        // log density / kinetic term of the two ends travel with them
+        const double lpo = C.lpO, keo = C.keO;
+        C.lpO = C.lpP;
+        C.keO = C.keP;
+        C.lpP = lpo;
+        C.keP = keo;
+      }
+      if (back) {   // rho = -rho (:245)
+#pragma unroll
+        for (int e = 0; e < E; ++e) v[e] = -v[e];
+      }
+      C.back = back;
+      C.weight = back ? C.wL : C.wR;      // :244,248
+      C.k = 0;
+      C.n_new = 1u << depth;
+      C.lse_ext = -INFINITY;
+      C.candValid = 0;
+      C.sub = 0;
+      st = PS_MACRO;
+      break;
+    } while (0);
+    if (st == PS_MACRO) do {  // one macro step of extend_orbit (:251-273): start the forward stable_steps search
+      C.k = C.k + 1u;
+      // registers: (theta, rho in integration convention, grad(theta)); lpO/keO are its lp and rho.M^-1.rho
+      const double lpS = C.lpO, keS = C.keO;
+      C.lpS = lpS;
+      C.keS = keS;
+      const double HS = -lpS + 0.5 * keS;
+      C.HS = HS;
+      C.p0 = -HS;                                  // :252
+      save_ck();                                   // S
+      C.phase = PK_STABLE_F;
+      C.n = 0;
+      C.Hmin = HS;                                 // :165
+      C.Hmax = HS;
+      start_pass(P.macro_step, 1u, true, false);
+      st = PS_RUN;
+      break;
+    } while (0);
     if (st == PS_EXIT) {
       if constexpr (Target::BLOCK_LOCKSTEP) continue;
       break;

@@ -438,604 +438,601 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
       st = ST_PASS_END;
     }
     // =============================== cold: per-chain state machine ==============================
-    while (st != ST_RUN && st != ST_EXIT) {
-      switch (st) {
-        case ST_CHAIN: {  // grab the next chain from the queue
-          uint32_t cidx = 0;
-          if (t == 0) cidx = atomicAdd(P.queue, 1u);
-          cidx = Grp::bcast0(cidx, &sh_bcast);
-          if (cidx >= (uint32_t)P.n_chains) {
-            st = ST_EXIT;
-            break;
-          }
-          C.chain = P.chain_offset + cidx;
-#pragma unroll
-          for (int e = 0; e < E; ++e) {
-            const int j = target.coord(e, t);
-            q[e] = (j < P.d) ? P.state[(size_t)cidx * P.d + j] : 0.0;
-          }
-          C.Hbig = P.Hstep ? P.Hstep[cidx] : P.H0;
-          C.delta = P.delta ? P.delta[cidx] : P.delta0;
-          if constexpr (ADAPT) {
-            const double* as = P.adapt_state + (size_t)cidx * WN_ADAPT_STRIDE;
-            C.Hbig = as[0];
-            C.delta = as[1];
-            C.p2npush = (int)as[2];
-#pragma unroll
-            for (int i = 0; i < 5; ++i) { C.p2q[i] = as[3 + i]; C.p2n[i] = (int)as[8 + i]; }
-            C.adNaN = (int)as[13];
-            C.adNhist = (int)as[14];
-          }
-          C.it = 0;
-          C.chainF = 0;
-          C.chainB = 0;
-          st = ST_ITER;
-          break;
-        }
-        case ST_ITER: {  // per-iteration setup, WALNUTS.py:196-276
-          RngKey key{P.seed_lo, P.seed_hi, C.chain, P.iter0 + (uint32_t)C.it};
-          C.iter = key.iter;
-          C.nseq = 0;
-          {
-            const double Hbig = C.Hbig;
-            C.jlo = __dmul_rn(Hbig, __dadd_rn(1.0, -P.jitter));   // WALNUTS.py:298
-            C.jhi = __dmul_rn(Hbig, __dadd_rn(1.0, P.jitter));
-          }
-          if constexpr (ADAPT) C.warm = (key.iter <= (uint32_t)P.warmup_iter) ? 1 : 0;   // :209
-          uint32_t dirbits = 0;
-          for (int k = 0; k < P.M; ++k) {
-            const double u = rng_uniform(key, STREAM_DIR, (uint32_t)k);   // B = floor(U(0,2)), :216
-            dirbits |= (u >= 0.5 ? 1u : 0u) << k;
-          }
-          C.dirbits = dirbits;
-          double x[1];
-          {
-            double ke = 0.0;
-            if constexpr (Target::PAIR_LAYOUT) {
-#pragma unroll
-              for (int e2 = 0; e2 < E2; ++e2) {   // v ~ N(0, I), :236
-                double z0, z1;
-                const int p = e2 * G + t;
-                rng_normal_pair(key, STREAM_MOM, (uint32_t)p, z0, z1);
-                v[2 * e2] = (2 * p < P.d) ? z0 : 0.0;
-                v[2 * e2 + 1] = (2 * p + 1 < P.d) ? z1 : 0.0;
-              }
-            } else {
-#pragma unroll
-              for (int e = 0; e < E; ++e) {       // same normals, addressed by coordinate
-                const int j = target.coord(e, t);
-                double z0 = 0.0, z1 = 0.0;
-                if (j < P.d) rng_normal_pair(key, STREAM_MOM, (uint32_t)(j >> 1), z0, z1);
-                v[e] = (j < P.d) ? ((j & 1) ? z1 : z0) : 0.0;
-              }
-            }
-#pragma unroll
-            for (int e = 0; e < E; ++e) ke = fma(v[e], v[e], ke);
-            if constexpr (Target::COOP) {
-              // the gradient at the current state (:249) is requested as a zero-length pass: h = 0 leaves
-              // (q, v) untouched and the cooperative evaluation fills g and the energy partial
-#pragma unroll
-              for (int e = 0; e < E; ++e) g[e] = 0.0;
-              C.phase = PH_INIT;
-              rsearch = false;
-              rh = 0.0;
-              start_pass(0);
-              st = ST_RUN;
-              break;
-            }
-            const double lpp = target.lp_grad(q, g, red, parity);        // :249
-            x[0] = fma(0.5, ke, -lpp);
-          }
-          Grp::template sum<1>(x, red, parity);
-          st = ST_ITER2;
-          C.H0 = x[0];
-          break;
-        }
-        case ST_ITER2: {  // second half of the per-iteration setup (after the gradient at the current state)
-          const double H0 = C.H0;                                         // :256
-          C.endH0 = H0;
-          C.endH1 = H0;
-#pragma unroll
-          for (int e2 = 0; e2 < E2; ++e2) {   // origin is both ends; it is also the first proposal
-            const double2 qq = make_double2(q[2 * e2], q[2 * e2 + 1]);
-            *sc(V_PARK_Q, e2) = qq;
-            *sc(V_PARK_V, e2) = make_double2(v[2 * e2], v[2 * e2 + 1]);
-            *sc(V_PARK_G, e2) = make_double2(g[2 * e2], g[2 * e2 + 1]);
-            *sc(V_PROP0, e2) = qq;
-            if (P.orbit_min) { *sc(V_OMIN, e2) = qq; *sc(V_OMAX, e2) = qq; }   // :274-276
-          }
-          C.propCur = 0;
-          C.lwtSum0 = 0.0; C.lwtSum1 = 0.0;
-          C.timeLen0 = 0.0; C.timeLen1 = 0.0;
-          C.maxInt0 = 0; C.maxInt1 = 0;
-          C.WoldSum = 1.0;
-          C.L_ = 0;
-          C.indexStat = 0.0;
-          C.orbitLen = 0.0; C.orbitLenSam = 0.0;
-          C.nF = 0; C.nB = 0;
-          C.NdS = 0; C.NdC = 0;
-          C.stopCode = 0;
-          C.bothPassive = 0;
-          C.forced = 0;
-          C.sN = 0; C.sNne = 0; C.sNz = 0;
-          C.sHmax = H0; C.sHmin = H0;
-          C.sHnan = 0;
-          C.side = -1;
-          C.xi = 1.0;
-          C.level = 0;
-          st = ST_LEVEL;
-          break;
-        }
-        case ST_LEVEL: {  // start doubling `level`, WALNUTS.py:281-294
-          const int level = C.level, side = C.side;
-          const int ns = (C.dirbits >> level) & 1u;   // 0 forward, 1 backward
-          const double nxi = ns ? -1.0 : 1.0;
-          if (side < 0) {
-            // registers hold the origin with forward-time v; switch to integration convention
-#pragma unroll
-            for (int e = 0; e < E; ++e) v[e] *= nxi;
-          } else if (ns != side) {
-            // swap the active end with the parked one (stored in forward-time convention)
-            const double xi = C.xi;
-#pragma unroll
-            for (int e2 = 0; e2 < E2; ++e2) {
-              const double2 pq = *sc(V_PARK_Q, e2), pv = *sc(V_PARK_V, e2), pg = *sc(V_PARK_G, e2);
-              *sc(V_PARK_Q, e2) = make_double2(q[2 * e2], q[2 * e2 + 1]);
-              *sc(V_PARK_V, e2) = make_double2(xi * v[2 * e2], xi * v[2 * e2 + 1]);
-              *sc(V_PARK_G, e2) = make_double2(g[2 * e2], g[2 * e2 + 1]);
-              q[2 * e2] = pq.x; q[2 * e2 + 1] = pq.y;
-              v[2 * e2] = nxi * pv.x; v[2 * e2 + 1] = nxi * pv.y;
-              g[2 * e2] = pg.x; g[2 * e2 + 1] = pg.y;
-            }
-          }
-          C.side = ns;
-          C.xi = nxi;
-          C.nleaf = 0;
-          C.n_new = 1u << level;
-          C.WnewSum = 0.0;
-          C.Lold = C.L_;
-          C.indexStatOld = C.indexStat;
-          C.candValid = 0;
-          st = ST_MACRO;
-          break;
-        }
-        case ST_MACRO: {  // start one macro step from the active end
-          const uint32_t nleaf = C.nleaf + 1u;
-          C.nleaf = nleaf;
-          double h;
-          if (C.level == 0) {
-            h = jit(useq());              // :298
-            C.orbitLen = C.orbitLen + h;  // :300
-          } else if (nleaf & 1u) {
-            h = jit(useq());              // :395 (two draws per leaf pair)
-            C.h2 = jit(useq());
-          } else {
-            h = C.h2;
-          }
-          C.h = h;
-          const double Ham0 = C.side ? C.endH1 : C.endH0;
-          C.Ham0 = Ham0;
-          C.phase = PH_FWD;
-          const int c0 = (P.kind == KIND_FIXED) ? 0 : P.minC;
-          C.c = c0;
-          rh = h; rc = c0; rlim = P.maxC; rHref = Ham0; rdelta = C.delta; rsign = 1.0;
-          rsearch = (P.kind != KIND_FIXED);
+    // Handlers are laid out in transition order (every transition goes DOWN this list), so one straight pass takes
+    // a chain from the end of a pass to the start of the next one, and the chains that share a warp (G < 32) run
+    // each handler TOGETHER instead of serialising a switch: pass end -> leaf -> level end -> iteration end ->
+    // next chain -> iteration setup -> level start -> macro-step start -> (hot loop).
+    if (st == ST_PASS_END) do {  // a pass of 2^c micro-steps finished
+      const bool unbounded = (smax & 0x7ff00000) >= LAZY_LIMIT ||
+                             ((umax & 0x80000000u) && (int)(umax & 0x7ff00000u) >= LAZY_LIMIT);
+      double x[2] = {hp, ((expmax == 0x7ff00000) ? 1.0 : 0.0) + (unbounded ? 1024.0 : 0.0)};
+      Grp::template sum<2>(x, red, parity);
+      const double Hend = x[0];
+      const bool redo_exact = Target::LAZY_ENERGY && x[1] >= 1024.0;
+      const bool anybad = x[1] != 0.0;
+      if (rsearch && !redo_exact) {
+        // fast path of the search (adaptiveIntegrators.py:69-94, 111-132): attempt failed -> next c
+        const bool ok = !anybad && fabs(rHref - Hend) < rdelta;
+        if (!ok && rc < rlim) {
+          rEv += evmul << rc;
+          ++rc;
           rexact = false;
-          rEv = 0;
-          if constexpr (ADAPT) trackH = C.warm && P.adaptH && (P.kind != KIND_FIXED);
-          if constexpr (Target::LAZY_ENERGY) rlazyok = target.lazy_ok && (C.jhi <= 1024.0);
-          if (P.kind != KIND_FIXED) save_ck();   // S = start state (integration convention)
-          C.wIntact = 1;
-          start_pass(c0);
+          load_ck(rsign);
+          start_pass(rc);
           st = ST_RUN;
           break;
         }
-        case ST_PASS_END: {  // a pass of 2^c micro-steps finished
-          const bool unbounded = (smax & 0x7ff00000) >= LAZY_LIMIT ||
-                                 ((umax & 0x80000000u) && (int)(umax & 0x7ff00000u) >= LAZY_LIMIT);
-          double x[2] = {hp, ((expmax == 0x7ff00000) ? 1.0 : 0.0) + (unbounded ? 1024.0 : 0.0)};
-          Grp::template sum<2>(x, red, parity);
-          const double Hend = x[0];
-          const bool redo_exact = Target::LAZY_ENERGY && x[1] >= 1024.0;
-          const bool anybad = x[1] != 0.0;
-          if (rsearch && !redo_exact) {
-            // fast path of the search (adaptiveIntegrators.py:69-94, 111-132): attempt failed -> next c
-            const bool ok = !anybad && fabs(rHref - Hend) < rdelta;
-            if (!ok && rc < rlim) {
-              rEv += evmul << rc;
-              ++rc;
-              rexact = false;
-              load_ck(rsign);
-              start_pass(rc);
-              st = ST_RUN;
-              break;
-            }
-          }
-          const int phase = C.phase;
-          if (Target::COOP && phase == PH_INIT) {   // gradient at the current state arrived: H0 = Hend
-            C.H0 = Hend;
-            st = ST_ITER2;
-            break;
-          }
-          if (rsearch) {   // leave the fast path: write the search state back
-            C.c = rc;
-            if (phase == PH_FWD) C.nF = C.nF + rEv; else C.nB = C.nB + rEv;
-            rEv = 0;
-          }
-          int c = C.c;
-          if (redo_exact) {
-            // a skipped energy might have been non-finite: repeat this pass with per-step energies
-            rexact = true;
-            load_ck(phase == PH_BWD ? -1.0 : 1.0);
-            start_pass(phase == PH_REDO ? C.cSim : c);
+      }
+      const int phase = C.phase;
+      if (Target::COOP && phase == PH_INIT) {   // gradient at the current state arrived: H0 = Hend
+        C.H0 = Hend;
+        st = ST_ITER2;
+        break;
+      }
+      if (rsearch) {   // leave the fast path: write the search state back
+        C.c = rc;
+        if (phase == PH_FWD) C.nF = C.nF + rEv; else C.nB = C.nB + rEv;
+        rEv = 0;
+      }
+      int c = C.c;
+      if (redo_exact) {
+        // a skipped energy might have been non-finite: repeat this pass with per-step energies
+        rexact = true;
+        load_ck(phase == PH_BWD ? -1.0 : 1.0);
+        start_pass(phase == PH_REDO ? C.cSim : c);
+        st = ST_RUN;
+        break;
+      }
+      rexact = false;
+      if (phase == PH_FWD) {
+        C.nF = C.nF + (evmul << c);
+        const bool ok = !anybad && fabs(C.Ham0 - Hend) < C.delta;   // adaptiveIntegrators.py:87-92
+        if (!(P.kind == KIND_FIXED || ok || c == P.maxC)) {
+          ++c;
+          C.c = c;
+          rc = c;
+          load_ck(1.0);
+          start_pass(c);
+          st = ST_RUN;
+          break;
+        }
+        C.If = c;
+        C.cSim = c;
+        C.lwtf = 0.0;
+        if (P.kind == KIND_R2P) {
+          if (useq() < P.p0) {              // adaptiveIntegrators.py:392
+            C.lwtf = P.log_p0;
+          } else {                          // :400-424 redo at If+1
+            C.cSim = c + 1;
+            C.phase = PH_REDO;
+            rsearch = false;
+            load_ck(1.0);
+            start_pass(c + 1);
             st = ST_RUN;
             break;
           }
-          rexact = false;
-          if (phase == PH_FWD) {
-            C.nF = C.nF + (evmul << c);
-            const bool ok = !anybad && fabs(C.Ham0 - Hend) < C.delta;   // adaptiveIntegrators.py:87-92
-            if (!(P.kind == KIND_FIXED || ok || c == P.maxC)) {
-              ++c;
-              C.c = c;
-              rc = c;
-              load_ck(1.0);
-              start_pass(c);
-              st = ST_RUN;
-              break;
-            }
-            C.If = c;
-            C.cSim = c;
-            C.lwtf = 0.0;
-            if (P.kind == KIND_R2P) {
-              if (useq() < P.p0) {              // adaptiveIntegrators.py:392
-                C.lwtf = P.log_p0;
-              } else {                          // :400-424 redo at If+1
-                C.cSim = c + 1;
-                C.phase = PH_REDO;
-                rsearch = false;
-                load_ck(1.0);
-                start_pass(c + 1);
-                st = ST_RUN;
-                break;
-              }
-            }
-          } else if (phase == PH_REDO) {
-            C.nF = C.nF + (evmul << C.cSim);
-            C.lwtf = P.log_1mp0;
-          }
-          if (phase != PH_BWD) {
-            // forward simulation done: registers hold the out state O
-            C.Hfwd = Hend;
-            if constexpr (ADAPT) {
-              if (C.warm && P.adaptH) {
-                if (P.kind == KIND_FIXED) {      // adaptiveIntegrators.py:59
-                  const double ad = fabs(C.Ham0 - Hend);
-                  C.igr = rh * pow((ad > 1.0e-10) ? ad : 1.0e-10, -1.0 / 3.0);
-                } else {                         // :101,399,424 (last forward pass)
-                  const double md = C.maxd;
-                  C.igr = (md > 0.0 || md != md) ? hh0 * pow(md, -1.0 / 3.0) : INFINITY;
-                }
-              }
-              trackH = false;
-            }
-            if (P.kind == KIND_FIXED) {
-              C.Ib = 0;
-              C.lwt = 0.0;
-              st = ST_LEAF;
-              break;
-            }
-            const int If = C.If, cSim = C.cSim;
-            int maxTry, Ib;
-            if (P.kind != KIND_R2P || cSim == If) { maxTry = If - 1; Ib = If; }   // :104-111 / :195-202 / :430-433
-            else { maxTry = P.maxC; Ib = P.maxC; }                              // :434-437
-            C.maxTry = maxTry;
-            C.Ib = Ib;
-            if (maxTry >= P.minC) {
-              save_ck();             // O replaces S
-              C.wIntact = 0;
-              C.phase = PH_BWD;
-              C.c = P.minC;
-              rc = P.minC; rlim = maxTry; rHref = Hend; rsign = -1.0; rsearch = true; rEv = 0;
-              if constexpr (ADAPT) trackH = false;
-#pragma unroll
-              for (int e = 0; e < E; ++e) v[e] = -v[e];
-              start_pass(P.minC);
-              st = ST_RUN;
-              break;
-            }
-          } else {
-            C.nB = C.nB + (evmul << c);
-            const bool ok = !anybad && fabs(C.Hfwd - Hend) < C.delta;   // :129-132 / :461-464
-            if (ok) C.Ib = c;
-            if (!ok && c < C.maxTry) {
-              ++c;
-              C.c = c;
-              rc = c;
-              load_ck(-1.0);
-              start_pass(c);
-              st = ST_RUN;
-              break;
+        }
+      } else if (phase == PH_REDO) {
+        C.nF = C.nF + (evmul << C.cSim);
+        C.lwtf = P.log_1mp0;
+      }
+      if (phase != PH_BWD) {
+        // forward simulation done: registers hold the out state O
+        C.Hfwd = Hend;
+        if constexpr (ADAPT) {
+          if (C.warm && P.adaptH) {
+            if (P.kind == KIND_FIXED) {      // adaptiveIntegrators.py:59
+              const double ad = fabs(C.Ham0 - Hend);
+              C.igr = rh * pow((ad > 1.0e-10) ? ad : 1.0e-10, -1.0 / 3.0);
+            } else {                         // :101,399,424 (last forward pass)
+              const double md = C.maxd;
+              C.igr = (md > 0.0 || md != md) ? hh0 * pow(md, -1.0 / 3.0) : INFINITY;
             }
           }
-          // macro step complete
-          {
-            const int If = C.If, Ib = C.Ib, cSim = C.cSim;
-            if (P.kind != KIND_R2P) {
-              C.lwt = (If != Ib) ? WN_LOG_ZERO : 0.0;                  // :136, :239
-            } else {
-              double lwtb = WN_LOG_ZERO;                               // :467-471
-              if (cSim == Ib) lwtb = P.log_p0;
-              else if (cSim == Ib + 1) lwtb = P.log_1mp0;
-              C.lwt = lwtb - C.lwtf;
-            }
-          }
-          if (!C.wIntact) load_ck(1.0);
+          trackH = false;
+        }
+        if (P.kind == KIND_FIXED) {
+          C.Ib = 0;
+          C.lwt = 0.0;
           st = ST_LEAF;
           break;
         }
-        case ST_LEAF: {  // driver bookkeeping after a macro step, WALNUTS.py:302-368,398-570
-          if constexpr (ADAPT) {
-            if (C.warm && P.adaptH) p2_push(log(C.igr));    // :313,347,411,454,498,541
-          }
-          const int level = C.level, side = C.side;
-          const uint32_t nleaf = C.nleaf;
-          const double h = C.h, Hfwd = C.Hfwd, lwt = C.lwt;
-          const int idx = (level == 0) ? (side ? -1 : 1) : (side ? C.maxInt1 - 1 : C.maxInt0 + 1);
-          const double tl = (level == 0) ? h : (side ? C.timeLen1 : C.timeLen0) + h;
-          if (side) { C.maxInt1 = idx; C.timeLen1 = tl; C.endH1 = Hfwd; }
-          else { C.maxInt0 = idx; C.timeLen0 = tl; C.endH0 = Hfwd; }
-          {  // running statistics over used steps
-            const int If = C.If, Ib = C.Ib;
-            const int cs = (P.kind == KIND_FIXED) ? 0 : C.cSim;
-            if (C.sN == 0) {
-              C.sMinIf = If; C.sMaxIf = If;
-              C.sMinC = cs; C.sMaxC = cs;
-              C.sMinL = lwt; C.sMaxL = lwt;
-            } else {
-              C.sMinIf = min(C.sMinIf, If); C.sMaxIf = max(C.sMaxIf, If);
-              C.sMinC = min(C.sMinC, cs); C.sMaxC = max(C.sMaxC, cs);
-              C.sMinL = fmin(C.sMinL, lwt); C.sMaxL = fmax(C.sMaxL, lwt);
-            }
-            C.sN = C.sN + 1;
-            C.sNne = C.sNne + (If != Ib);
-            C.sNz = C.sNz + (If == 0);
-            if (Hfwd != Hfwd) C.sHnan = 1;
-            else { C.sHmax = fmax(C.sHmax, Hfwd); C.sHmin = fmin(C.sHmin, Hfwd); }
-          }
-          if (!finite_d(Hfwd)) {   // forced reject, :316,350,414,457,501,544 (quirks A14 ii, iii)
-            C.forced = 1;
-            if (level == 0 || (nleaf & 1u)) C.stopCode = 999;
-            st = ST_ITER_END;
-            break;
-          }
-          double ls = side ? C.lwtSum1 : C.lwtSum0;
-          if (level == 0) ls = lwt;                                                  // :321,354
-          else if (!P.compat || !(side == 1 && !(nleaf & 1u))) ls += lwt;            // :420,507,550; quirk A14(i)
-          if (side) C.lwtSum1 = ls; else C.lwtSum0 = ls;
-          const double Wnew = exp(-Hfwd + C.H0 + ls);                                // :322,...
-          bool pick;
-          if (level == 0) {
-            C.WnewSum = Wnew;
-            pick = true;                                                            // :326,359
-          } else {
-            const double ws = C.WnewSum + Wnew;
-            C.WnewSum = ws;
-            pick = false;
-            if (ws > WN_WT_SUM_THRESH) pick = useq() < Wnew / ws;                    // :426,464,512,554
-            C.orbitLen = C.orbitLen + h;                                            // :432,...
-          }
-          if (pick) {
-            const int pv = V_PROP0 + (C.propCur ^ 1);
+        const int If = C.If, cSim = C.cSim;
+        int maxTry, Ib;
+        if (P.kind != KIND_R2P || cSim == If) { maxTry = If - 1; Ib = If; }   // :104-111 / :195-202 / :430-433
+        else { maxTry = P.maxC; Ib = P.maxC; }                              // :434-437
+        C.maxTry = maxTry;
+        C.Ib = Ib;
+        if (maxTry >= P.minC) {
+          save_ck();             // O replaces S
+          C.wIntact = 0;
+          C.phase = PH_BWD;
+          C.c = P.minC;
+          rc = P.minC; rlim = maxTry; rHref = Hend; rsign = -1.0; rsearch = true; rEv = 0;
+          if constexpr (ADAPT) trackH = false;
 #pragma unroll
-            for (int e2 = 0; e2 < E2; ++e2) *sc(pv, e2) = make_double2(q[2 * e2], q[2 * e2 + 1]);
-            C.candValid = 1;
-            C.L_ = idx;
-            C.indexStat = side ? -tl : tl;
-          }
-          if (P.orbit_min) {
-#pragma unroll
-            for (int e2 = 0; e2 < E2; ++e2) {
-              double2 lo = *sc(V_OMIN, e2), hi = *sc(V_OMAX, e2);
-              // np.minimum / np.maximum propagate NaN
-              lo.x = (q[2 * e2] < lo.x || q[2 * e2] != q[2 * e2]) ? q[2 * e2] : lo.x;
-              lo.y = (q[2 * e2 + 1] < lo.y || q[2 * e2 + 1] != q[2 * e2 + 1]) ? q[2 * e2 + 1] : lo.y;
-              hi.x = (q[2 * e2] > hi.x || q[2 * e2] != q[2 * e2]) ? q[2 * e2] : hi.x;
-              hi.y = (q[2 * e2 + 1] > hi.y || q[2 * e2 + 1] != q[2 * e2 + 1]) ? q[2 * e2 + 1] : hi.y;
-              *sc(V_OMIN, e2) = lo;
-              *sc(V_OMAX, e2) = hi;
-            }
-          }
-          bool sub = false;
-          if (level > 0) {
-            const double xi = C.xi;
-            if (nleaf & 1u) {
-              // left end of the pending dyadic levels 1..ctz(nleaf-1) (all when nleaf == 1)
-              const int lvl = (nleaf == 1u) ? level : (__ffs(nleaf - 1u) - 1);
-#pragma unroll
-              for (int e2 = 0; e2 < E2; ++e2) {
-                *sc(V_STACK + 2 * lvl, e2) = make_double2(q[2 * e2], q[2 * e2 + 1]);
-                *sc(V_STACK + 2 * lvl + 1, e2) = make_double2(xi * v[2 * e2], xi * v[2 * e2 + 1]);
-              }
-            } else {
-              // post-order sub-U-turn checks (WALNUTS.py:22-41 plan; :479,568,582)
-              for (int s = 1; s <= level && (nleaf & ((1u << s) - 1u)) == 0u; ++s) {
-                const uint32_t m = nleaf - (1u << s) + 1u;
-                const int lvl = (m == 1u) ? level : (__ffs(m - 1u) - 1);
-                if (uturn_vs(V_STACK + 2 * lvl, V_STACK + 2 * lvl + 1)) {
-                  sub = true;
-                  break;
-                }
-              }
-            }
-          }
-          if (sub) {                         // :597-605
-            C.candValid = 0;
-            C.L_ = C.Lold;
-            C.indexStat = C.indexStatOld;
-            C.NdS = level;
-            C.NdC = level + 1;
-            C.stopCode = 5;
-            st = ST_ITER_END;
-          } else {
-            st = (nleaf == C.n_new) ? ST_LEVEL_END : ST_MACRO;
-          }
+          for (int e = 0; e < E; ++e) v[e] = -v[e];
+          start_pass(P.minC);
+          st = ST_RUN;
           break;
         }
-        case ST_LEVEL_END: {  // WALNUTS.py:595-648
-          const int level = C.level;
-          const double ws = C.WnewSum, wo = C.WoldSum;
-          C.indexStat = C.indexStat / (C.timeLen0 + C.timeLen1);                     // :595
-          if (!(useq() < ws / wo)) {                                                 // :613
-            C.L_ = C.Lold;
-            C.indexStat = C.indexStatOld;
-          } else if (C.candValid) {
-            C.propCur = C.propCur ^ 1;
-          }
-          C.candValid = 0;
-          const bool joined = uturn_vs(V_PARK_Q, V_PARK_V);                          // :622
-          const bool bothPassive = (C.lwtSum1 < WN_LOG_ZERO + 1.0) && (C.lwtSum0 < WN_LOG_ZERO + 1.0);   // :624
-          C.bothPassive = bothPassive;
-          C.NdS = level + 1;
-          C.NdC = level + 1;
-          C.orbitLenSam = C.orbitLen;
-          if (joined || bothPassive) {
-            C.stopCode = joined ? 4 : -4;
-            st = ST_ITER_END;
-            break;
-          }
-          C.WoldSum = wo + ws;                                                       // :641
-          C.level = level + 1;
-          st = (level + 1 == P.M) ? ST_ITER_END : ST_LEVEL;
+      } else {
+        C.nB = C.nB + (evmul << c);
+        const bool ok = !anybad && fabs(C.Hfwd - Hend) < C.delta;   // :129-132 / :461-464
+        if (ok) C.Ib = c;
+        if (!ok && c < C.maxTry) {
+          ++c;
+          C.c = c;
+          rc = c;
+          load_ck(-1.0);
+          start_pass(c);
+          st = ST_RUN;
           break;
         }
-        case ST_ITER_END: {  // qc = qProp; outputs, WALNUTS.py:653-695
-          const int pv = V_PROP0 + ((C.forced && C.candValid) ? (C.propCur ^ 1) : C.propCur);
+      }
+      // macro step complete
+      {
+        const int If = C.If, Ib = C.Ib, cSim = C.cSim;
+        if (P.kind != KIND_R2P) {
+          C.lwt = (If != Ib) ? WN_LOG_ZERO : 0.0;                  // :136, :239
+        } else {
+          double lwtb = WN_LOG_ZERO;                               // :467-471
+          if (cSim == Ib) lwtb = P.log_p0;
+          else if (cSim == Ib + 1) lwtb = P.log_1mp0;
+          C.lwt = lwtb - C.lwtf;
+        }
+      }
+      if (!C.wIntact) load_ck(1.0);
+      st = ST_LEAF;
+      break;
+    } while (0);
+    if (st == ST_LEAF) do {  // driver bookkeeping after a macro step, WALNUTS.py:302-368,398-570
+      if constexpr (ADAPT) {
+        if (C.warm && P.adaptH) p2_push(log(C.igr));    // :313,347,411,454,498,541
+      }
+      const int level = C.level, side = C.side;
+      const uint32_t nleaf = C.nleaf;
+      const double h = C.h, Hfwd = C.Hfwd, lwt = C.lwt;
+      const int idx = (level == 0) ? (side ? -1 : 1) : (side ? C.maxInt1 - 1 : C.maxInt0 + 1);
+      const double tl = (level == 0) ? h : (side ? C.timeLen1 : C.timeLen0) + h;
+      if (side) { C.maxInt1 = idx; C.timeLen1 = tl; C.endH1 = Hfwd; }
+      else { C.maxInt0 = idx; C.timeLen0 = tl; C.endH0 = Hfwd; }
+      {  // running statistics over used steps
+        const int If = C.If, Ib = C.Ib;
+        const int cs = (P.kind == KIND_FIXED) ? 0 : C.cSim;
+        if (C.sN == 0) {
+          C.sMinIf = If; C.sMaxIf = If;
+          C.sMinC = cs; C.sMaxC = cs;
+          C.sMinL = lwt; C.sMaxL = lwt;
+        } else {
+          C.sMinIf = min(C.sMinIf, If); C.sMaxIf = max(C.sMaxIf, If);
+          C.sMinC = min(C.sMinC, cs); C.sMaxC = max(C.sMaxC, cs);
+          C.sMinL = fmin(C.sMinL, lwt); C.sMaxL = fmax(C.sMaxL, lwt);
+        }
+        C.sN = C.sN + 1;
+        C.sNne = C.sNne + (If != Ib);
+        C.sNz = C.sNz + (If == 0);
+        if (Hfwd != Hfwd) C.sHnan = 1;
+        else { C.sHmax = fmax(C.sHmax, Hfwd); C.sHmin = fmin(C.sHmin, Hfwd); }
+      }
+      if (!finite_d(Hfwd)) {   // forced reject, :316,350,414,457,501,544 (quirks A14 ii, iii)
+        C.forced = 1;
+        if (level == 0 || (nleaf & 1u)) C.stopCode = 999;
+        st = ST_ITER_END;
+        break;
+      }
+      double ls = side ? C.lwtSum1 : C.lwtSum0;
+      if (level == 0) ls = lwt;                                                  // :321,354
+      else if (!P.compat || !(side == 1 && !(nleaf & 1u))) ls += lwt;            // :420,507,550; quirk A14(i)
+      if (side) C.lwtSum1 = ls; else C.lwtSum0 = ls;
+      const double Wnew = exp(-Hfwd + C.H0 + ls);                                // :322,...
+      bool pick;
+      if (level == 0) {
+        C.WnewSum = Wnew;
+        pick = true;                                                            // :326,359
+      } else {
+        const double ws = C.WnewSum + Wnew;
+        C.WnewSum = ws;
+        pick = false;
+        if (ws > WN_WT_SUM_THRESH) pick = useq() < Wnew / ws;                    // :426,464,512,554
+        C.orbitLen = C.orbitLen + h;                                            // :432,...
+      }
+      if (pick) {
+        const int pv = V_PROP0 + (C.propCur ^ 1);
+#pragma unroll
+        for (int e2 = 0; e2 < E2; ++e2) *sc(pv, e2) = make_double2(q[2 * e2], q[2 * e2 + 1]);
+        C.candValid = 1;
+        C.L_ = idx;
+        C.indexStat = side ? -tl : tl;
+      }
+      if (P.orbit_min) {
+#pragma unroll
+        for (int e2 = 0; e2 < E2; ++e2) {
+          double2 lo = *sc(V_OMIN, e2), hi = *sc(V_OMAX, e2);
+          // np.minimum / np.maximum propagate NaN
+          lo.x = (q[2 * e2] < lo.x || q[2 * e2] != q[2 * e2]) ? q[2 * e2] : lo.x;
+          lo.y = (q[2 * e2 + 1] < lo.y || q[2 * e2 + 1] != q[2 * e2 + 1]) ? q[2 * e2 + 1] : lo.y;
+          hi.x = (q[2 * e2] > hi.x || q[2 * e2] != q[2 * e2]) ? q[2 * e2] : hi.x;
+          hi.y = (q[2 * e2 + 1] > hi.y || q[2 * e2 + 1] != q[2 * e2 + 1]) ? q[2 * e2 + 1] : hi.y;
+          *sc(V_OMIN, e2) = lo;
+          *sc(V_OMAX, e2) = hi;
+        }
+      }
+      bool sub = false;
+      if (level > 0) {
+        const double xi = C.xi;
+        if (nleaf & 1u) {
+          // left end of the pending dyadic levels 1..ctz(nleaf-1) (all when nleaf == 1)
+          const int lvl = (nleaf == 1u) ? level : (__ffs(nleaf - 1u) - 1);
 #pragma unroll
           for (int e2 = 0; e2 < E2; ++e2) {
-            const double2 qq = *sc(pv, e2);
-            q[2 * e2] = qq.x;
-            q[2 * e2 + 1] = qq.y;
+            *sc(V_STACK + 2 * lvl, e2) = make_double2(q[2 * e2], q[2 * e2 + 1]);
+            *sc(V_STACK + 2 * lvl + 1, e2) = make_double2(xi * v[2 * e2], xi * v[2 * e2 + 1]);
           }
-          const uint32_t cidx = C.chain - P.chain_offset;
-          const int it = C.it;
-          const size_t row = (size_t)it * P.n_chains + cidx;
-          if (P.draws) {
-#pragma unroll
-            for (int e = 0; e < E; ++e) {
-              const int j = target.coord(e, t);
-              if (j < P.dg) P.draws[row * P.dg + j] = q[e];
+        } else {
+          // post-order sub-U-turn checks (WALNUTS.py:22-41 plan; :479,568,582)
+          for (int s = 1; s <= level && (nleaf & ((1u << s) - 1u)) == 0u; ++s) {
+            const uint32_t m = nleaf - (1u << s) + 1u;
+            const int lvl = (m == 1u) ? level : (__ffs(m - 1u) - 1);
+            if (uturn_vs(V_STACK + 2 * lvl, V_STACK + 2 * lvl + 1)) {
+              sub = true;
+              break;
             }
           }
-          if (P.orbit_min) {
+        }
+      }
+      if (sub) {                         // :597-605
+        C.candValid = 0;
+        C.L_ = C.Lold;
+        C.indexStat = C.indexStatOld;
+        C.NdS = level;
+        C.NdC = level + 1;
+        C.stopCode = 5;
+        st = ST_ITER_END;
+      } else {
+        st = (nleaf == C.n_new) ? ST_LEVEL_END : ST_MACRO;
+      }
+      break;
+    } while (0);
+    if (st == ST_LEVEL_END) do {  // WALNUTS.py:595-648
+      const int level = C.level;
+      const double ws = C.WnewSum, wo = C.WoldSum;
+      C.indexStat = C.indexStat / (C.timeLen0 + C.timeLen1);                     // :595
+      if (!(useq() < ws / wo)) {                                                 // :613
+        C.L_ = C.Lold;
+        C.indexStat = C.indexStatOld;
+      } else if (C.candValid) {
+        C.propCur = C.propCur ^ 1;
+      }
+      C.candValid = 0;
+      const bool joined = uturn_vs(V_PARK_Q, V_PARK_V);                          // :622
+      const bool bothPassive = (C.lwtSum1 < WN_LOG_ZERO + 1.0) && (C.lwtSum0 < WN_LOG_ZERO + 1.0);   // :624
+      C.bothPassive = bothPassive;
+      C.NdS = level + 1;
+      C.NdC = level + 1;
+      C.orbitLenSam = C.orbitLen;
+      if (joined || bothPassive) {
+        C.stopCode = joined ? 4 : -4;
+        st = ST_ITER_END;
+        break;
+      }
+      C.WoldSum = wo + ws;                                                       // :641
+      C.level = level + 1;
+      st = (level + 1 == P.M) ? ST_ITER_END : ST_LEVEL;
+      break;
+    } while (0);
+    if (st == ST_ITER_END) do {  // qc = qProp; outputs, WALNUTS.py:653-695
+      const int pv = V_PROP0 + ((C.forced && C.candValid) ? (C.propCur ^ 1) : C.propCur);
 #pragma unroll
-            for (int e2 = 0; e2 < E2; ++e2) {
-              const double2 lo = *sc(V_OMIN, e2), hi = *sc(V_OMAX, e2);
-              const int j0 = target.coord(2 * e2, t), j1 = target.coord(2 * e2 + 1, t);
-              if (j0 < P.dg) { P.orbit_min[row * P.dg + j0] = lo.x; P.orbit_max[row * P.dg + j0] = hi.x; }
-              if (j1 < P.dg) { P.orbit_min[row * P.dg + j1] = lo.y; P.orbit_max[row * P.dg + j1] = hi.y; }
+      for (int e2 = 0; e2 < E2; ++e2) {
+        const double2 qq = *sc(pv, e2);
+        q[2 * e2] = qq.x;
+        q[2 * e2 + 1] = qq.y;
+      }
+      const uint32_t cidx = C.chain - P.chain_offset;
+      const int it = C.it;
+      const size_t row = (size_t)it * P.n_chains + cidx;
+      if (P.draws) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          const int j = target.coord(e, t);
+          if (j < P.dg) P.draws[row * P.dg + j] = q[e];
+        }
+      }
+      if (P.orbit_min) {
+#pragma unroll
+        for (int e2 = 0; e2 < E2; ++e2) {
+          const double2 lo = *sc(V_OMIN, e2), hi = *sc(V_OMAX, e2);
+          const int j0 = target.coord(2 * e2, t), j1 = target.coord(2 * e2 + 1, t);
+          if (j0 < P.dg) { P.orbit_min[row * P.dg + j0] = lo.x; P.orbit_max[row * P.dg + j0] = hi.x; }
+          if (j1 < P.dg) { P.orbit_min[row * P.dg + j1] = lo.y; P.orbit_max[row * P.dg + j1] = hi.y; }
+        }
+      }
+      const unsigned long long nF = C.nF, nB = C.nB;
+      if (P.diag && t == 0) {
+        double* dg = P.diag + row * 24;
+        const double n = (double)C.sN;
+        dg[0] = C.L_; dg[1] = C.NdS; dg[2] = C.orbitLen; dg[3] = C.orbitLenSam;
+        dg[4] = C.maxInt0; dg[5] = C.maxInt1; dg[6] = (double)nF; dg[7] = (double)nB;
+        dg[8] = C.sMinIf; dg[9] = C.sMaxIf; dg[10] = C.sMinL; dg[11] = C.sMaxL;
+        dg[12] = C.bothPassive ? 1.0 : 0.0;
+        dg[13] = ((C.lwtSum1 < WN_LOG_ZERO + 1.0) || (C.lwtSum0 < WN_LOG_ZERO + 1.0)) ? 1.0 : 0.0;
+        dg[14] = (double)C.sNne / n; dg[15] = C.Hbig; dg[16] = (double)C.sNz / n;
+        dg[17] = C.sHnan ? __longlong_as_double(0x7ff8000000000000ll) : C.sHmax - C.sHmin;
+        dg[18] = C.delta; dg[19] = C.stopCode; dg[20] = C.NdC; dg[21] = C.sMinC; dg[22] = C.sMaxC;
+        dg[23] = C.indexStat;
+      }
+      if constexpr (ADAPT) {
+        if (C.warm) {   // WALNUTS.py:701-712
+          double delta = C.delta;
+          if (P.adaptDelta) {
+            const double fac = (C.sHnan ? __longlong_as_double(0x7ff8000000000000ll) : C.sHmax - C.sHmin) / delta;  // :704
+            double* hrow = P.adapt_hist + (size_t)cidx * P.warmup_iter;
+            const int n0 = C.adNhist;             // finite / infinite entries stored so far (sorted)
+            int pos = n0;
+            if (fac != fac) {
+              C.adNaN = 1;
+            } else {                              // upper-bound position in the sorted row
+              int lo = 0, hi = n0;
+              while (lo < hi) { const int mid = (lo + hi) >> 1; if (hrow[mid] <= fac) lo = mid + 1; else hi = mid; }
+              pos = lo;
             }
-          }
-          const unsigned long long nF = C.nF, nB = C.nB;
-          if (P.diag && t == 0) {
-            double* dg = P.diag + row * 24;
-            const double n = (double)C.sN;
-            dg[0] = C.L_; dg[1] = C.NdS; dg[2] = C.orbitLen; dg[3] = C.orbitLenSam;
-            dg[4] = C.maxInt0; dg[5] = C.maxInt1; dg[6] = (double)nF; dg[7] = (double)nB;
-            dg[8] = C.sMinIf; dg[9] = C.sMaxIf; dg[10] = C.sMinL; dg[11] = C.sMaxL;
-            dg[12] = C.bothPassive ? 1.0 : 0.0;
-            dg[13] = ((C.lwtSum1 < WN_LOG_ZERO + 1.0) || (C.lwtSum0 < WN_LOG_ZERO + 1.0)) ? 1.0 : 0.0;
-            dg[14] = (double)C.sNne / n; dg[15] = C.Hbig; dg[16] = (double)C.sNz / n;
-            dg[17] = C.sHnan ? __longlong_as_double(0x7ff8000000000000ll) : C.sHmax - C.sHmin;
-            dg[18] = C.delta; dg[19] = C.stopCode; dg[20] = C.NdC; dg[21] = C.sMinC; dg[22] = C.sMaxC;
-            dg[23] = C.indexStat;
-          }
-          if constexpr (ADAPT) {
-            if (C.warm) {   // WALNUTS.py:701-712
-              double delta = C.delta;
-              if (P.adaptDelta) {
-                const double fac = (C.sHnan ? __longlong_as_double(0x7ff8000000000000ll) : C.sHmax - C.sHmin) / delta;  // :704
-                double* hrow = P.adapt_hist + (size_t)cidx * P.warmup_iter;
-                const int n0 = C.adNhist;             // finite / infinite entries stored so far (sorted)
-                int pos = n0;
-                if (fac != fac) {
-                  C.adNaN = 1;
-                } else {                              // upper-bound position in the sorted row
-                  int lo = 0, hi = n0;
-                  while (lo < hi) { const int mid = (lo + hi) >> 1; if (hrow[mid] <= fac) lo = mid + 1; else hi = mid; }
-                  pos = lo;
-                }
-                const int n1 = (fac != fac) ? n0 : n0 + 1;
-                // element i of the row after insertion, read from the row before insertion
-                auto at = [&](int i) -> double { return (fac != fac || i < pos) ? hrow[i] : (i == pos ? fac : hrow[i - 1]); };
-                const int iterN = (int)C.iter;
-                double newdelta = delta;
-                if (iterN > 10) {                     // :705-707, np.quantile(x[0:iterN], q) (method 'linear')
-                  double qv;
-                  if (C.adNaN) {
-                    qv = __longlong_as_double(0x7ff8000000000000ll);
-                  } else {
-                    const double nn = (double)n1, qq = P.adQuant;
-                    // numpy _compute_virtual_index(n, q, 1, 1): n*q + (1 + q*(1-1-1)) - 1
-                    const double virt = __dadd_rn(__dadd_rn(__dmul_rn(nn, qq), __dadd_rn(1.0, __dmul_rn(qq, -1.0))), -1.0);
-                    int prev = (int)floor(virt), next = prev + 1;
-                    if (virt >= nn - 1.0) { prev = n1 - 1; next = n1 - 1; }
-                    if (prev < 0) { prev = 0; }
-                    if (next < 0) { next = 0; }
-                    const double gam = virt - floor(virt);
-                    const double a = at(prev), b = at(next);
-                    const double dba = b - a;                                   // numpy _lerp
-                    qv = (gam >= 0.5) ? (b - dba * (1.0 - gam)) : (a + dba * gam);
-                  }
-                  newdelta = P.adTarget / qv;
-                }
-                if constexpr (G > 32) __syncthreads(); else if constexpr (G > 1) __syncwarp(Grp::mask());
-                if (t == 0 && fac == fac) {           // shift the tail and insert
-                  for (int i = n0; i > pos; --i) hrow[i] = hrow[i - 1];
-                  hrow[pos] = fac;
-                }
-                if constexpr (G > 32) __syncthreads(); else if constexpr (G > 1) __syncwarp(Grp::mask());
-                C.adNhist = n1;
-                delta = newdelta;
-                C.delta = delta;
+            const int n1 = (fac != fac) ? n0 : n0 + 1;
+            // element i of the row after insertion, read from the row before insertion
+            auto at = [&](int i) -> double { return (fac != fac || i < pos) ? hrow[i] : (i == pos ? fac : hrow[i - 1]); };
+            const int iterN = (int)C.iter;
+            double newdelta = delta;
+            if (iterN > 10) {                     // :705-707, np.quantile(x[0:iterN], q) (method 'linear')
+              double qv;
+              if (C.adNaN) {
+                qv = __longlong_as_double(0x7ff8000000000000ll);
+              } else {
+                const double nn = (double)n1, qq = P.adQuant;
+                // numpy _compute_virtual_index(n, q, 1, 1): n*q + (1 + q*(1-1-1)) - 1
+                const double virt = __dadd_rn(__dadd_rn(__dmul_rn(nn, qq), __dadd_rn(1.0, __dmul_rn(qq, -1.0))), -1.0);
+                int prev = (int)floor(virt), next = prev + 1;
+                if (virt >= nn - 1.0) { prev = n1 - 1; next = n1 - 1; }
+                if (prev < 0) { prev = 0; }
+                if (next < 0) { next = 0; }
+                const double gam = virt - floor(virt);
+                const double a = at(prev), b = at(next);
+                const double dba = b - a;                                   // numpy _lerp
+                qv = (gam >= 0.5) ? (b - dba * (1.0 - gam)) : (a + dba * gam);
               }
-              if (P.adaptH && C.p2npush > 10) C.Hbig = pow(delta, 1.0 / 3.0) * exp(C.p2q[2]);   // :711-712
+              newdelta = P.adTarget / qv;
             }
+            if constexpr (G > 32) __syncthreads(); else if constexpr (G > 1) __syncwarp(Grp::mask());
+            if (t == 0 && fac == fac) {           // shift the tail and insert
+              for (int i = n0; i > pos; --i) hrow[i] = hrow[i - 1];
+              hrow[pos] = fac;
+            }
+            if constexpr (G > 32) __syncthreads(); else if constexpr (G > 1) __syncwarp(Grp::mask());
+            C.adNhist = n1;
+            delta = newdelta;
+            C.delta = delta;
           }
-          const unsigned long long cf = C.chainF + nF, cbk = C.chainB + nB;
-          C.chainF = cf;
-          C.chainB = cbk;
-          C.it = it + 1;
-          if (it + 1 < P.n_iter) {
-            st = ST_ITER;
-            break;
-          }
+          if (P.adaptH && C.p2npush > 10) C.Hbig = pow(delta, 1.0 / 3.0) * exp(C.p2q[2]);   // :711-712
+        }
+      }
+      const unsigned long long cf = C.chainF + nF, cbk = C.chainB + nB;
+      C.chainF = cf;
+      C.chainB = cbk;
+      C.it = it + 1;
+      if (it + 1 < P.n_iter) {
+        st = ST_ITER;
+        break;
+      }
 #pragma unroll
-          for (int e = 0; e < E; ++e) {
+      for (int e = 0; e < E; ++e) {
+        const int j = target.coord(e, t);
+        if (j < P.d) P.state[(size_t)cidx * P.d + j] = q[e];
+      }
+      if (t == 0) {
+        if (P.nevalF) P.nevalF[cidx] = cf;
+        if (P.nevalB) P.nevalB[cidx] = cbk;
+        if constexpr (ADAPT) {
+          double* as = P.adapt_state + (size_t)cidx * WN_ADAPT_STRIDE;
+          as[0] = C.Hbig; as[1] = C.delta; as[2] = (double)C.p2npush;
+#pragma unroll
+          for (int i = 0; i < 5; ++i) { as[3 + i] = C.p2q[i]; as[8 + i] = (double)C.p2n[i]; }
+          as[13] = (double)C.adNaN; as[14] = (double)C.adNhist;
+        }
+      }
+      totF += cf;
+      totB += cbk;
+      st = ST_CHAIN;
+      break;
+    } while (0);
+    if (st == ST_CHAIN) do {  // grab the next chain from the queue
+      uint32_t cidx = 0;
+      if (t == 0) cidx = atomicAdd(P.queue, 1u);
+      cidx = Grp::bcast0(cidx, &sh_bcast);
+      if (cidx >= (uint32_t)P.n_chains) {
+        st = ST_EXIT;
+        break;
+      }
+      C.chain = P.chain_offset + cidx;
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const int j = target.coord(e, t);
+        q[e] = (j < P.d) ? P.state[(size_t)cidx * P.d + j] : 0.0;
+      }
+      C.Hbig = P.Hstep ? P.Hstep[cidx] : P.H0;
+      C.delta = P.delta ? P.delta[cidx] : P.delta0;
+      if constexpr (ADAPT) {
+        const double* as = P.adapt_state + (size_t)cidx * WN_ADAPT_STRIDE;
+        C.Hbig = as[0];
+        C.delta = as[1];
+        C.p2npush = (int)as[2];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) { C.p2q[i] = as[3 + i]; C.p2n[i] = (int)as[8 + i]; }
+        C.adNaN = (int)as[13];
+        C.adNhist = (int)as[14];
+      }
+      C.it = 0;
+      C.chainF = 0;
+      C.chainB = 0;
+      st = ST_ITER;
+      break;
+    } while (0);
+    if (st == ST_ITER) do {  // per-iteration setup, WALNUTS.py:196-276
+      RngKey key{P.seed_lo, P.seed_hi, C.chain, P.iter0 + (uint32_t)C.it};
+      C.iter = key.iter;
+      C.nseq = 0;
+      {
+        const double Hbig = C.Hbig;
+        C.jlo = __dmul_rn(Hbig, __dadd_rn(1.0, -P.jitter));   // WALNUTS.py:298
+        C.jhi = __dmul_rn(Hbig, __dadd_rn(1.0, P.jitter));
+      }
+      if constexpr (ADAPT) C.warm = (key.iter <= (uint32_t)P.warmup_iter) ? 1 : 0;   // :209
+      uint32_t dirbits = 0;
+      for (int k = 0; k < P.M; ++k) {
+        const double u = rng_uniform(key, STREAM_DIR, (uint32_t)k);   // B = floor(U(0,2)), :216
+        dirbits |= (u >= 0.5 ? 1u : 0u) << k;
+      }
+      C.dirbits = dirbits;
+      double x[1];
+      {
+        double ke = 0.0;
+        if constexpr (Target::PAIR_LAYOUT) {
+#pragma unroll
+          for (int e2 = 0; e2 < E2; ++e2) {   // v ~ N(0, I), :236
+            double z0, z1;
+            const int p = e2 * G + t;
+            rng_normal_pair(key, STREAM_MOM, (uint32_t)p, z0, z1);
+            v[2 * e2] = (2 * p < P.d) ? z0 : 0.0;
+            v[2 * e2 + 1] = (2 * p + 1 < P.d) ? z1 : 0.0;
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < E; ++e) {       // same normals, addressed by coordinate
             const int j = target.coord(e, t);
-            if (j < P.d) P.state[(size_t)cidx * P.d + j] = q[e];
+            double z0 = 0.0, z1 = 0.0;
+            if (j < P.d) rng_normal_pair(key, STREAM_MOM, (uint32_t)(j >> 1), z0, z1);
+            v[e] = (j < P.d) ? ((j & 1) ? z1 : z0) : 0.0;
           }
-          if (t == 0) {
-            if (P.nevalF) P.nevalF[cidx] = cf;
-            if (P.nevalB) P.nevalB[cidx] = cbk;
-            if constexpr (ADAPT) {
-              double* as = P.adapt_state + (size_t)cidx * WN_ADAPT_STRIDE;
-              as[0] = C.Hbig; as[1] = C.delta; as[2] = (double)C.p2npush;
+        }
 #pragma unroll
-              for (int i = 0; i < 5; ++i) { as[3 + i] = C.p2q[i]; as[8 + i] = (double)C.p2n[i]; }
-              as[13] = (double)C.adNaN; as[14] = (double)C.adNhist;
-            }
-          }
-          totF += cf;
-          totB += cbk;
-          st = ST_CHAIN;
+        for (int e = 0; e < E; ++e) ke = fma(v[e], v[e], ke);
+        if constexpr (Target::COOP) {
+          // the gradient at the current state (:249) is requested as a zero-length pass: h = 0 leaves
+          // (q, v) untouched and the cooperative evaluation fills g and the energy partial
+#pragma unroll
+          for (int e = 0; e < E; ++e) g[e] = 0.0;
+          C.phase = PH_INIT;
+          rsearch = false;
+          rh = 0.0;
+          start_pass(0);
+          st = ST_RUN;
           break;
         }
-        default:
-          st = ST_EXIT;
-          break;
+        const double lpp = target.lp_grad(q, g, red, parity);        // :249
+        x[0] = fma(0.5, ke, -lpp);
       }
-    }
+      Grp::template sum<1>(x, red, parity);
+      st = ST_ITER2;
+      C.H0 = x[0];
+      break;
+    } while (0);
+    if (st == ST_ITER2) do {  // second half of the per-iteration setup (after the gradient at the current state)
+      const double H0 = C.H0;                                         // :256
+      C.endH0 = H0;
+      C.endH1 = H0;
+#pragma unroll
+      for (int e2 = 0; e2 < E2; ++e2) {   // origin is both ends; it is also the first proposal
+        const double2 qq = make_double2(q[2 * e2], q[2 * e2 + 1]);
+        *sc(V_PARK_Q, e2) = qq;
+        *sc(V_PARK_V, e2) = make_double2(v[2 * e2], v[2 * e2 + 1]);
+        *sc(V_PARK_G, e2) = make_double2(g[2 * e2], g[2 * e2 + 1]);
+        *sc(V_PROP0, e2) = qq;
+        if (P.orbit_min) { *sc(V_OMIN, e2) = qq; *sc(V_OMAX, e2) = qq; }   // :274-276
+      }
+      C.propCur = 0;
+      C.lwtSum0 = 0.0; C.lwtSum1 = 0.0;
+      C.timeLen0 = 0.0; C.timeLen1 = 0.0;
+      C.maxInt0 = 0; C.maxInt1 = 0;
+      C.WoldSum = 1.0;
+      C.L_ = 0;
+      C.indexStat = 0.0;
+      C.orbitLen = 0.0; C.orbitLenSam = 0.0;
+      C.nF = 0; C.nB = 0;
+      C.NdS = 0; C.NdC = 0;
+      C.stopCode = 0;
+      C.bothPassive = 0;
+      C.forced = 0;
+      C.sN = 0; C.sNne = 0; C.sNz = 0;
+      C.sHmax = H0; C.sHmin = H0;
+      C.sHnan = 0;
+      C.side = -1;
+      C.xi = 1.0;
+      C.level = 0;
+      st = ST_LEVEL;
+      break;
+    } while (0);
+    if (st == ST_LEVEL) do {  // start doubling `level`, WALNUTS.py:281-294
+      const int level = C.level, side = C.side;
+      const int ns = (C.dirbits >> level) & 1u;   // 0 forward, 1 backward
+      const double nxi = ns ? -1.0 : 1.0;
+      if (side < 0) {
+        // registers hold the origin with forward-time v; switch to integration convention
+#pragma unroll
+        for (int e = 0; e < E; ++e) v[e] *= nxi;
+      } else if (ns != side) {
+        // swap the active end with the parked one (stored in forward-time convention)
+        const double xi = C.xi;
+#pragma unroll
+        for (int e2 = 0; e2 < E2; ++e2) {
+          const double2 pq = *sc(V_PARK_Q, e2), pv = *sc(V_PARK_V, e2), pg = *sc(V_PARK_G, e2);
+          *sc(V_PARK_Q, e2) = make_double2(q[2 * e2], q[2 * e2 + 1]);
+          *sc(V_PARK_V, e2) = make_double2(xi * v[2 * e2], xi * v[2 * e2 + 1]);
+          *sc(V_PARK_G, e2) = make_double2(g[2 * e2], g[2 * e2 + 1]);
+          q[2 * e2] = pq.x; q[2 * e2 + 1] = pq.y;
+          v[2 * e2] = nxi * pv.x; v[2 * e2 + 1] = nxi * pv.y;
+          g[2 * e2] = pg.x; g[2 * e2 + 1] = pg.y;
+        }
+      }
+      C.side = ns;
+      C.xi = nxi;
+      C.nleaf = 0;
+      C.n_new = 1u << level;
+      C.WnewSum = 0.0;
+      C.Lold = C.L_;
+      C.indexStatOld = C.indexStat;
+      C.candValid = 0;
+      st = ST_MACRO;
+      break;
+    } while (0);
+    if (st == ST_MACRO) do {  // start one macro step from the active end
+      const uint32_t nleaf = C.nleaf + 1u;
+      C.nleaf = nleaf;
+      double h;
+      if (C.level == 0) {
+        h = jit(useq());              // :298
+        C.orbitLen = C.orbitLen + h;  // :300
+      } else if (nleaf & 1u) {
+        h = jit(useq());              // :395 (two draws per leaf pair)
+        C.h2 = jit(useq());
+      } else {
+        h = C.h2;
+      }
+      C.h = h;
+      const double Ham0 = C.side ? C.endH1 : C.endH0;
+      C.Ham0 = Ham0;
+      C.phase = PH_FWD;
+      const int c0 = (P.kind == KIND_FIXED) ? 0 : P.minC;
+      C.c = c0;
+      rh = h; rc = c0; rlim = P.maxC; rHref = Ham0; rdelta = C.delta; rsign = 1.0;
+      rsearch = (P.kind != KIND_FIXED);
+      rexact = false;
+      rEv = 0;
+      if constexpr (ADAPT) trackH = C.warm && P.adaptH && (P.kind != KIND_FIXED);
+      if constexpr (Target::LAZY_ENERGY) rlazyok = target.lazy_ok && (C.jhi <= 1024.0);
+      if (P.kind != KIND_FIXED) save_ck();   // S = start state (integration convention)
+      C.wIntact = 1;
+      start_pass(c0);
+      st = ST_RUN;
+      break;
+    } while (0);
     if (st == ST_EXIT) {
       if constexpr (Target::BLOCK_LOCKSTEP || Target::COOP) continue;   // keep serving the block's barriers
       break;
