@@ -74,3 +74,22 @@ def test_package_value_errors(cuda_lib):
         wb.walnuts(None, np.zeros(3), tg, tg, np.ones(3), 1.0, 5, -0.1, 0, 1, seed=1)
     with pytest.raises(TypeError):
         wb.walnuts(None, np.zeros(3), lambda q: 0.0, lambda q: q, np.ones(3), 1.0, 5, 0.1, 0, 1, seed=1)
+
+
+def test_package_mode_rejects_diagnostics_and_reports_evals(cuda_lib):
+    from walnuts_b200 import ChainBatch
+    with ChainBatch("std_normal", 3, 4, mode="package", H0=1.0, delta=0.2, M=5, seed=1, data={"inv_mass": np.ones(3)}) as cb:
+        cb.set_state(np.zeros((4, 3)))
+        with pytest.raises(ValueError, match="WALNUTSPY mode only"):
+            cb.run(1, diag=True)
+        out = cb.run(2)
+        assert (out["nevalF"] > 0).all() and out["draws"].shape == (2, 4, 3)
+        mean, var = cb.moments()
+        q = cb.get_state()
+        assert np.allclose(mean, q.mean(0)) and np.allclose(var, q.var(0, ddof=1))
+
+
+def test_fp64_peak_microbenchmark(cuda_lib):
+    from walnuts_b200 import fp64_peak
+    peak = fp64_peak(0)
+    assert 5e12 < peak < 6e13        # B200: ~34 TFLOP/s measured, 37 nominal

@@ -274,16 +274,15 @@ struct StockWatsonT {
   __device__ __forceinline__ double lp_grad(const double (&q)[E], double (&g)[E], double* red, int& parity) const {
     const int t = threadIdx.x % G;
     const int k0 = t * B;
+    // (temporaries are kept to 8 arrays of B doubles: the kernel is register-bound)
     // ---- phase 1: prefix sums of the innovations; index-0 entries and tS travel as "base" channels ----
     double locZ[B], locX[B];
     double ch[5] = {0.0, 0.0, 0.0, 0.0, 0.0}, ex1[5];
 #pragma unroll
     for (int i = 0; i < B; ++i) {
       const int k = k0 + i;
-      const double zi = (k >= 1 && k <= T - 2) ? q[i] : 0.0;
-      const double xi = (k >= 1 && k <= T - 1) ? q[B + i] : 0.0;
-      ch[0] += zi;
-      ch[1] += xi;
+      ch[0] += (k >= 1 && k <= T - 2) ? q[i] : 0.0;
+      ch[1] += (k >= 1 && k <= T - 1) ? q[B + i] : 0.0;
       locZ[i] = ch[0];      // local inclusive prefix
       locX[i] = ch[1];
     }
@@ -291,17 +290,19 @@ struct StockWatsonT {
     scan<5, true>(ch, ex1, red, parity);
     const double Z0 = ch[2], X0 = ch[3], tS = ch[4];
     const double sigma = exp(-0.5 * tS), etS = exp(tS);
-    double z[B], ez[B], xx[B], w[B], c[B];
+    double lp = 0.0;
+    double ez[B], w[B], c[B], locC[B];
     double ch2[2] = {0.0, 0.0}, ex2[2];
     const double ez_prev = exp(0.5 * fma(sigma, ex1[0], Z0));   // exp(z_{k0-1}/2)
-    double locC[B];
 #pragma unroll
     for (int i = 0; i < B; ++i) {
       const int k = k0 + i;
-      z[i] = fma(sigma, ex1[0] + locZ[i], Z0);
-      xx[i] = fma(sigma, ex1[1] + locX[i], X0);
-      ez[i] = exp(0.5 * z[i]);
-      w[i] = exp(-xx[i]);
+      ez[i] = exp(0.5 * fma(sigma, ex1[0] + locZ[i], Z0));
+      const double xx = fma(sigma, ex1[1] + locX[i], X0);
+      w[i] = exp(-xx);
+      if (k <= T - 1) lp -= 0.5 * xx;
+      if (k >= 1 && k <= T - 2) lp -= 0.5 * q[i] * q[i];
+      if (k >= 1 && k <= T - 1) lp -= 0.5 * (q[B + i] * q[B + i] + q[2 * B + i] * q[2 * B + i]);
       const double ezm = (i == 0) ? ez_prev : ez[(i > 0) ? i - 1 : 0];
       c[i] = (k >= 1 && k <= T - 1) ? ezm * q[2 * B + i] : 0.0;   // exp(z_{k-1}/2) * tauinn_{k-1}
       ch2[0] += c[i];
@@ -311,51 +312,35 @@ struct StockWatsonT {
     // ---- phase 2: tau ----
     scan<2, true>(ch2, ex2, red, parity);
     const double U0 = ch2[1];
-    double lp = 0.0;
-    double r[B], a[B];
+    // residuals and their local suffix sums in one reverse sweep
+    double sufR[B], sufA[B];
     double ch3[2] = {0.0, 0.0}, ex3[2];
 #pragma unroll
-    for (int i = 0; i < B; ++i) {
+    for (int i = B - 1; i >= 0; --i) {
       const int k = k0 + i;
       const bool obs = (k <= T - 1);
-      const double tau = U0 + (ex2[0] + locC[i]);
-      const double e = y[i] - tau;
+      const double e = y[i] - (U0 + (ex2[0] + locC[i]));
       const double eew = e * e * w[i];
-      r[i] = obs ? e * w[i] : 0.0;
-      a[i] = obs ? (-0.5 + 0.5 * eew) : 0.0;
-      if (obs) lp += -0.5 * xx[i] - 0.5 * eew;
-      if (k >= 1 && k <= T - 2) lp -= 0.5 * q[i] * q[i];
-      if (k >= 1 && k <= T - 1) lp -= 0.5 * (q[B + i] * q[B + i] + q[2 * B + i] * q[2 * B + i]);
-    }
-    // local suffix sums
-    double sufR[B], sufA[B];
-#pragma unroll
-    for (int i = B - 1; i >= 0; --i) {
-      ch3[0] += r[i];
-      ch3[1] += a[i];
+      if (obs) lp -= 0.5 * eew;
+      ch3[0] += obs ? e * w[i] : 0.0;
+      ch3[1] += obs ? (-0.5 + 0.5 * eew) : 0.0;
       sufR[i] = ch3[0];
       sufA[i] = ch3[1];
     }
     // ---- phase 3: R, A suffix sums ----
     scan<2, false>(ch3, ex3, red, parity);
-    double bb[B], Rk[B], Ak[B];
-    double ch4[2] = {0.0, 0.0}, ex4[2];
-#pragma unroll
-    for (int i = 0; i < B; ++i) {
-      Rk[i] = ex3[0] + sufR[i];
-      Ak[i] = ex3[1] + sufA[i];
-      bb[i] = 0.5 * c[i] * Rk[i];            // b_{k-1} of appendix B (c is already masked)
-    }
     double sufB[B];
+    double ch4[2] = {0.0, 0.0}, ex4[2];
 #pragma unroll
     for (int i = B - 1; i >= 0; --i) {
       const int k = k0 + i;
-      sufB[i] = ch4[0];                       // exclusive local suffix
-      ch4[0] += bb[i];
+      const double bb = 0.5 * c[i] * (ex3[0] + sufR[i]);     // b_{k-1} of appendix B (c is already masked)
+      sufB[i] = ch4[0];                                      // exclusive local suffix
+      ch4[0] += bb;
       // d/dtS partial: sum_k zinn_k Bz_{k+1} + sum_k xinn_k A_{k+1}, with the first sum re-ordered as
       // sum_j b_j * (prefix of zinn before j)
       const double pzex = (ex1[0] + locZ[i]) - ((k >= 1 && k <= T - 2) ? q[i] : 0.0);
-      ch4[1] += bb[i] * pzex + ((k >= 1 && k <= T - 1) ? q[B + i] * Ak[i] : 0.0);
+      ch4[1] += bb * pzex + ((k >= 1 && k <= T - 1) ? q[B + i] * (ex3[1] + sufA[i]) : 0.0);
     }
     // ---- phase 4: Bz suffix sums and the tS total ----
     scan<2, false>(ch4, ex4, red, parity);
@@ -363,10 +348,11 @@ struct StockWatsonT {
     for (int i = 0; i < B; ++i) {
       const int k = k0 + i;
       const double Sx = ex4[0] + sufB[i];     // sum_{j > k} bb_j = Bz of appendix B at the next index
+      const double Rk = ex3[0] + sufR[i], Ak = ex3[1] + sufA[i];
       const double ezm = (i == 0) ? ez_prev : ez[(i > 0) ? i - 1 : 0];
       g[i] = (k == 0) ? Sx : ((k <= T - 2) ? fma(sigma, Sx, -q[i]) : 0.0);
-      g[B + i] = (k == 0) ? Ak[i] : ((k <= T - 1) ? fma(sigma, Ak[i], -q[B + i]) : 0.0);
-      g[2 * B + i] = (k == 0) ? Rk[i] : ((k <= T - 1) ? fma(ezm, Rk[i], -q[2 * B + i]) : 0.0);
+      g[B + i] = (k == 0) ? Ak : ((k <= T - 1) ? fma(sigma, Ak, -q[B + i]) : 0.0);
+      g[2 * B + i] = (k == 0) ? Rk : ((k <= T - 1) ? fma(ezm, Rk, -q[2 * B + i]) : 0.0);
     }
     g[3 * B] = (t == 0) ? (5.0 - 0.5 * etS - 0.5 * sigma * ch4[1]) : 0.0;
     g[3 * B + 1] = 0.0;
