@@ -308,7 +308,9 @@ def main():
         "gpu_launches": args.steps * cb.last_launches(),
         "clocks": clocks,
         "roofline": {"bound": "fp64", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                     "traffic": 0.98e9 * (evals / max(1, args.steps)) / 3.26e8,   # ncu dram bytes, scaled by evals
+                     # dram__bytes_read+write of one `ncu --set full` launch (0.98 GB for 3.26e8 evaluations,
+                     # profiles/r01_walnutspy_diag1000_R2P.txt), scaled to the evaluations of one bench launch
+                     "traffic": 0.98e9 * (evals / max(1, args.steps)) / 3.26e8,
                      "flop_per_eval": FLOP_PER_DIM_PER_EVAL * D, "achieved_at_12_flop_per_coord": ach * 12 / 8,
                      "peak_source": peak_src,
                      "note": "register-resident chains: FP64 FMA pipe bound, not HBM (SURVEY.md 8d); "
@@ -317,8 +319,16 @@ def main():
     }
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(args.cpu_iters)
+        if min_ess:
+            # identical transition kernel on identical streams (parity tests) => identical ESS per gradient
+            # evaluation; the CPU's min-ESS/sec is therefore its evals/s times the measured ESS per evaluation
+            per_eval = min_ess / evals_all
+            line["min_ess_per_grad_eval"] = per_eval
+            line["cpu_baseline"]["min_ess_per_sec"] = per_eval * line["cpu_baseline"]["value"]
         try:
             line["cpu_baseline_c"] = cpu_baseline_c(args.cpu_iters)
+            if min_ess:
+                line["cpu_baseline_c"]["min_ess_per_sec"] = min_ess / evals_all * line["cpu_baseline_c"]["value"]
         except Exception as e:                                   # the C checker is optional for the bench
             line["cpu_baseline_c"] = {"unavailable": str(e)[:200]}
     print(json.dumps(line))
