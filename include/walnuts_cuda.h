@@ -58,6 +58,10 @@ extern "C" {
 #define WN_INT_D 1     /* adaptiveIntegrators.adaptLeapFrogD    :65-137                      */
 #define WN_INT_R2P 2   /* adaptiveIntegrators.adaptLeapFrogR2P  :361-475                     */
 #define WN_INT_YOSHIDA 3 /* adaptiveIntegrators.adaptYoshidaD   :142-240 (4th-order triple)  */
+#define WN_INT_FLOW 4     /* adaptiveIntegrators.adaptLeapFrogFlowD      :246-356 (flow-error criterion)      */
+#define WN_INT_MIDPOINT 5 /* adaptiveIntegrators.adaptImplicitMidpointD  :478-641 (fixed-point iterations;
+                             FPNewton=True, which needs a Hessian, is not built)                            */
+#define WN_INT_RESCALED 6 /* adaptiveIntegrators.adaptRescaledLeapFrogD  :660-762 (per-dimension rescaling)  */
 
 #define WN_DIAG_COLS 24 /* WALNUTS.py:180,670-693 */
 
@@ -101,6 +105,10 @@ void wn_destroy(wn_handle* h);
  * [n_chains] (per-chain macro step / tolerance, overriding cfg.H0 / cfg.delta).
  * `on_device` != 0: `ptr` is a device pointer on cfg.device. */
 int wn_set_data(wn_handle* h, const char* key, const double* ptr, int64_t n, int on_device);
+
+/* Remaining integratorAuxPar fields (adaptiveIntegrators.py:36-44) used by WN_INT_MIDPOINT / WN_INT_RESCALED:
+ * `key` = "maxFPiter" (default 30), "FPtol" (1e-8), "rescaledGradThresh" (5.0). */
+int wn_set_aux(wn_handle* h, const char* key, double value);
 
 /* Warm-up adaptation of the macro step H and the tolerance delta, per chain, as reference
  * WALNUTS.py:136-147 (setup), :313 (P-squared quantile of log igrConst, P2quantile.py:16-92) and

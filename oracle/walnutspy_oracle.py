@@ -24,6 +24,7 @@ LOG_ZERO = -700.0                       # constants.py:13
 WT_SUM_THRESH = float(np.exp(LOG_ZERO + 1.0))   # constants.py:14
 
 FIXED, ADAPT_D, ADAPT_R2P, ADAPT_YOSHIDA = 0, 1, 2, 3
+ADAPT_FLOW, ADAPT_MIDPOINT, ADAPT_RESCALED = 4, 5, 6   # adaptiveIntegrators.py:246-356, :478-641, :660-762
 Y_FIRSTLAST = 1.351207191959658       # adaptiveIntegrators.py:143-144
 Y_MIDDLE = -1.702414383919315
 
@@ -31,8 +32,9 @@ Y_MIDDLE = -1.702414383919315
 class AuxPar:
     """adaptiveIntegrators.integratorAuxPar (adaptiveIntegrators.py:36-44), hot-path fields."""
 
-    def __init__(self, minC=0, maxC=10, R2Pprob0=2.0 / 3.0):
+    def __init__(self, minC=0, maxC=10, R2Pprob0=2.0 / 3.0, maxFPiter=30, FPtol=1.0e-8, rescaledGradThresh=5.0):
         self.minC, self.maxC, self.R2Pprob0 = minC, maxC, R2Pprob0
+        self.maxFPiter, self.FPtol, self.rescaledGradThresh = maxFPiter, FPtol, rescaledGradThresh
 
 
 def _pysum(x):
@@ -77,9 +79,226 @@ def _pass(q, vv, g, h, c, lpFun, track, yoshida=False):
     return q, vv, g, f, Hprev, ok, maxd, hh
 
 
+def _pymax(a, b):
+    # Python builtin max(a, b): b only if b > a (a NaN in `a` sticks, a NaN in `b` is dropped)
+    return b if b > a else a
+
+
+def _flow_pass(q, vv, g, h, c, lpFun, H0):
+    """One attempt of adaptLeapFrogFlowD (adaptiveIntegrators.py:252-287 / :309-339): 2**c leapfrog
+    micro-steps, each followed by a midpoint gradient and the 4 flow-error norms.
+    Returns (q, vv, g, f, H_last, all_finite, maxErr, max|diff H|, hh)."""
+    nstep = 2 ** c
+    hh = h / nstep
+    Hprev = H0
+    ok = True
+    maxd = 0.0
+    maxErr = None
+    f = None
+    for _ in range(nstep):
+        vh = vv + 0.5 * hh * g
+        qold, gold, vold = q, g, vv
+        q = q + hh * vh
+        f, g = lpFun(q)
+        vv = vh + 0.5 * hh * g
+        qMid = 0.5 * (q + qold) + (hh / 8.0) * (vold - vv)
+        _, gMid = lpFun(qMid)
+        qf = qold + hh * vold + hh * hh * ((1.0 / 6.0) * gold + (1.0 / 3.0) * gMid)
+        err = np.max(np.abs(qf - q))
+        vf = vold + (hh / 6.0) * (gold + g + 4.0 * gMid)
+        err = _pymax(err, np.max(np.abs(vf - vv)))
+        qb = q - hh * vv + hh * hh * ((1.0 / 6.0) * g + (1.0 / 3.0) * gMid)
+        err = _pymax(err, np.max(np.abs(qb - qold)))
+        vb = -(-vv + (hh / 6.0) * (gold + g + 4.0 * gMid))
+        err = _pymax(err, np.max(np.abs(vb - vold)))
+        # np.max(Errs) (:282,337) propagates NaN
+        maxErr = err if maxErr is None or (err > maxErr or err != err) else maxErr
+        Hk = -f + 0.5 * _pysum(vv * vv)
+        ok = ok and bool(np.isfinite(Hk))
+        dd = abs(Hk - Hprev)
+        maxd = dd if (dd > maxd or dd != dd) else maxd
+        Hprev = Hk
+    return q, vv, g, f, Hprev, ok, maxErr, maxd, hh
+
+
+def _macro_flow(q, v, g, Ham0, h, xi, lpFun, delta, aux):
+    """adaptLeapFrogFlowD, adaptiveIntegrators.py:246-356 (the search starts at c = 0, not minC)."""
+    vv0 = xi * v
+    nF = 0
+    If = aux.maxC
+    for c in range(0, aux.maxC + 1):                # :250-287
+        qq, vv, gg, f, Hl, ok, maxErr, maxd, hh = _flow_pass(q, vv0, g, h, c, lpFun, Ham0)
+        nF += 2 * 2 ** c
+        if ok and maxErr < delta:
+            If = c
+            break
+    with np.errstate(all="ignore"):
+        igr = hh * (maxd ** (-1.0 / 3.0)) if maxd > 0 else np.inf      # :294
+    Ib = If
+    nB = 0
+    for c in range(0, If):                          # :300-345
+        _, _, _, _, _, okb, maxErrb, _, _ = _flow_pass(qq, -vv, gg, h, c, lpFun, Hl)
+        nB += 2 * 2 ** c
+        if okb and maxErrb < delta:
+            Ib = c
+            break
+    return dict(q=qq, v=xi * vv, grad=gg, H=Hl, nF=nF, nB=nB, If=If, Ib=Ib, c=If, lwt=(If != Ib) * LOG_ZERO,
+                igrConst=igr)
+
+
+def _midpoint_pass(q, vv, g, h, c, lpFun, H0, aux):
+    """One attempt of adaptImplicitMidpointD with fixed-point iterations (FPNewton=False),
+    adaptiveIntegrators.py:483-541 / :572-626.  Returns (q, vv, g, f, H_last, all_finite, completed,
+    converged_last, max|diff Hams|, hh, n_evals); Hams of steps that were not completed are 0 (:490)."""
+    nstep = 2 ** c
+    hh = h / nstep
+    Hams = np.zeros(nstep + 1)
+    Hams[0] = H0
+    nev = 0
+    f = None
+    completed = 0
+    converged = False
+    for i in range(1, nstep + 1):
+        qt = q + hh * (vv + 0.5 * hh * g)            # :494
+        converged = False
+        oldMaxErr = 1.0e100
+        for _ in range(aux.maxFPiter):               # :500-523
+            mpq = 0.5 * (qt + q)
+            _, gmp = lpFun(mpq)
+            qtNew = q + hh * vv + (0.5 * hh * hh) * gmp
+            nev += 1
+            maxErr = np.max(np.abs(qtNew - qt))
+            qt = qtNew
+            if maxErr < aux.FPtol:
+                converged = True
+                break
+            if maxErr > 1.1 * oldMaxErr:
+                break
+            oldMaxErr = maxErr
+        if not converged:                            # :525-527
+            break
+        mpq = 0.5 * (qt + q)                         # :530-540
+        _, gmp = lpFun(mpq)
+        nev += 1
+        q = q + hh * vv + (0.5 * hh * hh) * gmp
+        vv = vv + hh * gmp
+        f, g = lpFun(q)
+        nev += 1
+        Hams[i] = -f + 0.5 * _pysum(vv * vv)
+        completed += 1
+    ok = bool(np.all(np.isfinite(Hams)))
+    with np.errstate(all="ignore"):
+        maxd = float(np.max(np.abs(np.diff(Hams))))
+    return q, vv, g, f, float(Hams[-1]), ok, completed == nstep, converged, maxd, hh, nev
+
+
+def _macro_midpoint(q, v, g, Ham0, h, xi, lpFun, delta, aux):
+    """adaptImplicitMidpointD, adaptiveIntegrators.py:478-641, fixed-point variant.  The reference ends the
+    PROCESS (`sys.exit()`, :548-550) when the last attempt (c = maxC) holds a step whose fixed-point iteration
+    did not converge; here that macro step reports a NaN energy, which the driver turns into a forced reject
+    (stop code 999) -- the same convention as the CUDA kernel (deviations)."""
+    vv0 = xi * v
+    nF = 0
+    If = aux.maxC
+    for c in range(0, aux.maxC + 1):                # :482-545
+        qq, vv, gg, f, Hl, ok, full, conv, maxd, hh, nev = _midpoint_pass(q, vv0, g, h, c, lpFun, Ham0, aux)
+        nF += nev
+        if ok and abs(Ham0 - Hl) < delta and full:
+            If = c
+            break
+    if not conv:                                    # :548-550 (sys.exit in the reference)
+        return dict(q=qq, v=xi * vv, grad=gg, H=float("nan"), nF=nF, nB=0, If=If, Ib=If, c=If, lwt=0.0,
+                    igrConst=float("nan"))
+    with np.errstate(all="ignore"):
+        igr = hh * (maxd ** (-1.0 / 3.0)) if maxd > 0 else np.inf      # :561
+    HO = -f + 0.5 * _pysum(vv * vv)                 # :569 (same expression as Hams[-1])
+    Ib = aux.maxC                                   # :564
+    nB = 0
+    for c in range(0, aux.maxC + 1):                # :570-633: the FULL range, not only c < If
+        _, _, _, _, Hb, okb, fullb, _, _, _, nev = _midpoint_pass(qq, -vv, gg, h, c, lpFun, HO, aux)
+        nB += nev
+        if okb and abs(HO - Hb) < delta and fullb:
+            Ib = c
+            break
+    return dict(q=qq, v=xi * vv, grad=gg, H=HO, nF=nF, nB=nB, If=If, Ib=Ib, c=If, lwt=(If != Ib) * LOG_ZERO,
+                igrConst=igr)
+
+
+def _rescaled_attempt(q, vv, g, h, Sd, lpFun):
+    """One leapfrog step in coordinates rescaled by Sd, adaptiveIntegrators.py:672-682 / :723-733."""
+    qb = q / Sd
+    gb = Sd * g
+    vh = vv + 0.5 * h * gb
+    qbn = qb + h * vh
+    q1 = qbn * Sd
+    ff, gnew = lpFun(q1)
+    gb1 = Sd * gnew
+    v1 = vh + 0.5 * h * gb1
+    gbmean = 0.5 * (np.abs(gb) + np.abs(gb1))
+    Ham1 = -ff + 0.5 * _pysum(v1 * v1)
+    return q1, v1, ff, gnew, gbmean, Ham1
+
+
+def _macro_rescaled(q, v, g, Ham0, h, xi, lpFun, delta, aux):
+    """adaptRescaledLeapFrogD, adaptiveIntegrators.py:660-762 (its debugging prints at :720-721 are not
+    reproduced)."""
+    d = q.size
+    thr = aux.rescaledGradThresh
+    Sd = np.ones(d)
+    Sred = np.zeros(d, dtype=np.int64)
+    vv = xi * v
+    If = aux.maxC
+    nF = nB = 0
+    for c in range(0, aux.maxC + 1):                # :669-700
+        q1, v1, ff, gnew, gbmean, Ham1 = _rescaled_attempt(q, vv, g, h, Sd, lpFun)
+        nF += 1
+        big = gbmean > thr
+        if not np.isfinite(Ham1):
+            Sred += 1
+        elif np.any(big):
+            Sred[big] += 1
+        elif abs(Ham0 - Ham1) > delta:
+            Sred += 1
+        else:
+            If = c
+            break
+        Sd = 2.0 ** (-Sred)
+    qO, vO, gO, HO = q1, v1, gnew, Ham1
+    SredForw = Sred
+    Sd = np.ones(d)
+    Sred = np.zeros(d, dtype=np.int64)
+    Ib = If
+    if If > 0:                                      # :718-755
+        for c in range(0, aux.maxC + 1):
+            _, _, _, _, gbmean, Ham1 = _rescaled_attempt(qO, -vO, gO, h, Sd, lpFun)
+            nB += 1
+            big = gbmean > thr
+            if not np.isfinite(Ham1):
+                Sred += 1
+            elif np.any(big):
+                Sred[big] += 1
+            elif abs(HO - Ham1) > delta:
+                Sred += 1
+            else:
+                Ib = c
+                break
+            if np.all(SredForw == Sred):
+                Ib = c + 1
+                break
+            Sd = 2.0 ** (-Sred)
+    lwt = LOG_ZERO * (not np.all(Sred == SredForw))     # :762
+    return dict(q=qO, v=xi * vO, grad=gO, H=HO, nF=nF, nB=nB, If=If, Ib=Ib, c=If, lwt=lwt, igrConst=1.0)
+
+
 def macro_step(kind, q, v, g, Ham0, h, xi, lpFun, delta, aux, rng):
     """One macro step.  Returns dict(q, v, grad, H, nF, nB, If, Ib, c, lwt, igrConst).
     `v` is in forward-time convention in and out (adaptiveIntegrators.py:73,135)."""
+    if kind == ADAPT_FLOW:
+        return _macro_flow(q, v, g, Ham0, h, xi, lpFun, delta, aux)
+    if kind == ADAPT_MIDPOINT:
+        return _macro_midpoint(q, v, g, Ham0, h, xi, lpFun, delta, aux)
+    if kind == ADAPT_RESCALED:
+        return _macro_rescaled(q, v, g, Ham0, h, xi, lpFun, delta, aux)
     vv0 = xi * v
     if kind == FIXED:                               # adaptiveIntegrators.py:49-59
         vh = vv0 + 0.5 * h * g

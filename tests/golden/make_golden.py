@@ -19,7 +19,8 @@ from oracle import package_oracle as po   # noqa: E402
 from oracle import ref_loader             # noqa: E402
 
 OUT = os.path.dirname(os.path.abspath(__file__))
-NAMES = {"fixed": "fixedLeapFrog", "D": "adaptLeapFrogD", "R2P": "adaptLeapFrogR2P"}
+NAMES = {"fixed": "fixedLeapFrog", "D": "adaptLeapFrogD", "R2P": "adaptLeapFrogR2P", "Yoshida": "adaptYoshidaD",
+         "Flow": "adaptLeapFrogFlowD", "Midpoint": "adaptImplicitMidpointD", "Rescaled": "adaptRescaledLeapFrogD"}
 
 
 def walnutspy_cases():
@@ -35,6 +36,14 @@ def walnutspy_cases():
                           delta=0.3, M=12 if integ != "fixed" else 10, n_iter=100, minC=0, maxC=10, seed=12, chain=1))
         cases.append(dict(name=f"wpy_corr_{integ}", target="corr_gauss", q0=np.array([1.0, 0.0]), integrator=integ,
                           H0=0.9, delta=0.1, M=8, n_iter=100, minC=1, maxC=10, seed=13, chain=0))
+    # the remaining integrators of adaptiveIntegrators.py (added after the cases above; the
+    # generator state is re-seeded so that the earlier fixtures stay byte-identical)
+    rng2 = np.random.default_rng(2026)
+    for integ, dlt in (("Yoshida", 0.05), ("Flow", 0.02), ("Midpoint", 0.05), ("Rescaled", 0.3)):
+        cases.append(dict(name=f"wpy_std7_{integ}", target="std_normal", q0=0.3 * rng2.standard_normal(7),
+                          integrator=integ, H0=1.1, delta=dlt, M=7, n_iter=60, minC=0, maxC=10, seed=21, chain=2))
+        cases.append(dict(name=f"wpy_funnel10_{integ}", target="funnel", q0=fq.copy(), integrator=integ, H0=0.4,
+                          delta=dlt, M=8, n_iter=40, minC=0, maxC=10, seed=22, chain=4))
     cases.append(dict(name="wpy_std100_R2P", target="std_normal", q0=rng.standard_normal(100), integrator="R2P",
                       H0=0.9 * 100 ** -0.25, delta=0.3, M=8, n_iter=40, minC=0, maxC=10, seed=14, chain=7))
     return cases
@@ -54,11 +63,15 @@ def package_cases():
 
 
 def main():
+    only = sys.argv[1:]          # optional name prefixes: regenerate only the matching fixtures
+    want = (lambda name: any(name.startswith(p) for p in only)) if only else (lambda name: True)
     wn, ai, td = ref_loader.load_walnutspy()
     pkg = ref_loader.load_package()
     tt = ref_loader.load_test_targets()
     lp = {"std_normal": td.stdGauss, "funnel": td.funnel10, "corr_gauss": td.corrGauss}
     for c in walnutspy_cases():
+        if not want(c["name"]):
+            continue
         t0 = time.time()
         s, d = ref_loader.run_walnutspy(lp[c["target"]], c["q0"], NAMES[c["integrator"]], c["H0"], c["delta"],
                                         c["n_iter"], c["M"], c["minC"], c["maxC"], seed=c["seed"], chain=c["chain"])
@@ -69,6 +82,8 @@ def main():
     plp = {"std_normal": (tt.standard_normal_lpdf, tt.standard_normal_grad),
            "funnel_pkg": (tt.funnel_lpdf, tt.funnel_grad)}
     for c in package_cases():
+        if not want(c["name"]):
+            continue
         t0 = time.time()
         rng = po.KeyedPackageRNG(c["seed"], c["chain"])
         f, g = plp[c["target"]]

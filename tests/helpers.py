@@ -31,7 +31,8 @@ def oracle_target(name, d, data=None):
     raise KeyError(name)
 
 
-KIND = {"fixed": wo.FIXED, "D": wo.ADAPT_D, "R2P": wo.ADAPT_R2P, "Yoshida": wo.ADAPT_YOSHIDA}
+KIND = {"fixed": wo.FIXED, "D": wo.ADAPT_D, "R2P": wo.ADAPT_R2P, "Yoshida": wo.ADAPT_YOSHIDA,
+        "Flow": wo.ADAPT_FLOW, "Midpoint": wo.ADAPT_MIDPOINT, "Rescaled": wo.ADAPT_RESCALED}
 
 
 def oracle_walnutspy(name, q0, integrator, H0, delta, M, n_iter, seed, chains, minC=0, maxC=10, data=None,

@@ -184,7 +184,9 @@ def test_walnutspy_golden_from_real_reference(cuda_lib, path):
     z = np.load(path)
     m = json.loads(str(z["meta"]))
     tg = {"std_normal": wb.targets.stdGauss, "funnel": wb.targets.funnel10, "corr_gauss": wb.targets.corrGauss}[m["target"]]
-    ig = {"fixed": wb.fixedLeapFrog, "D": wb.adaptLeapFrogD, "R2P": wb.adaptLeapFrogR2P}[m["integrator"]]
+    ig = {"fixed": wb.fixedLeapFrog, "D": wb.adaptLeapFrogD, "R2P": wb.adaptLeapFrogR2P, "Yoshida": wb.adaptYoshidaD,
+          "Flow": wb.adaptLeapFrogFlowD, "Midpoint": wb.adaptImplicitMidpointD,
+          "Rescaled": wb.adaptRescaledLeapFrogD}[m["integrator"]]
     aux = wb.integratorAuxPar(minC=m["minC"], maxC=m["maxC"])
     ref_s, ref_d = z["samples"], z["diagnostics"]
     kw = dict(integrator=ig, H0=m["H0"], delta0=m["delta"], warmupIter=0, M=m["M"], igrAux=aux, adaptH=False,

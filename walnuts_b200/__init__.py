@@ -10,9 +10,10 @@ from ._ffi import WalnutsError  # noqa: F401
 from .sampler import ChainBatch, fp64_peak  # noqa: F401
 from . import targets, integrators  # noqa: F401
 from .integrators import (fixedLeapFrog, adaptLeapFrogD, adaptLeapFrogR2P, adaptYoshidaD,  # noqa: F401
-                          integratorAuxPar)
+                          adaptLeapFrogFlowD, adaptImplicitMidpointD, adaptRescaledLeapFrogD, integratorAuxPar)
 from .api import WALNUTS, walnuts, walnuts_step  # noqa: F401
 
 __all__ = ["ChainBatch", "WALNUTS", "walnuts", "walnuts_step", "targets", "integrators",
-           "fixedLeapFrog", "adaptLeapFrogD", "adaptLeapFrogR2P", "adaptYoshidaD", "integratorAuxPar",
+           "fixedLeapFrog", "adaptLeapFrogD", "adaptLeapFrogR2P", "adaptYoshidaD", "adaptLeapFrogFlowD",
+           "adaptImplicitMidpointD", "adaptRescaledLeapFrogD", "integratorAuxPar",
            "WalnutsError", "fp64_peak"]

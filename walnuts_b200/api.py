@@ -43,8 +43,11 @@ def WALNUTS(lpFun, q0, generated=None, integrator=_ig.fixedLeapFrog, H0=0.2, ste
                                   "orbit statistics are kept for the coordinates themselves (generated=None)")
     if not isinstance(integrator, _ig._Integrator):
         raise TypeError("integrator must be one of walnuts_b200.fixedLeapFrog / adaptLeapFrogD / adaptLeapFrogR2P / "
-                        "adaptYoshidaD")
+                        "adaptYoshidaD / adaptLeapFrogFlowD / adaptImplicitMidpointD / adaptRescaledLeapFrogD")
     aux = igrAux or _ig.integratorAuxPar()
+    if integrator is _ig.adaptImplicitMidpointD and getattr(aux, "FPNewton", False):
+        raise NotImplementedError("adaptImplicitMidpointD with FPNewton=True needs the target's Hessian "
+                                  "(adaptiveIntegrators.py:503-506); only the fixed-point variant runs on the GPU")
     q0 = np.asarray(q0, dtype=np.float64)
     single = q0.ndim == 1
     q = q0.reshape(1, -1) if single else q0
@@ -56,6 +59,8 @@ def WALNUTS(lpFun, q0, generated=None, integrator=_ig.fixedLeapFrog, H0=0.2, ste
                     jitter=stepSizeRandScale, delta=delta0, M=M, minC=aux.minC, maxC=aux.maxC,
                     r2p_prob0=aux.R2Pprob0, seed=seed, chain_offset=chain_offset, device=device,
                     compat=compat, data=data) as cb:
+        cb.set_aux(getattr(aux, "maxFPiter", None), getattr(aux, "FPtol", None),
+                   getattr(aux, "rescaledGradThresh", None))
         if warmupIter > 0 and (adaptH or adaptDelta):
             cb.set_adapt(min(warmupIter, numIter), adaptH, adaptHtarget, adaptDelta, adaptDeltaTarget,
                          adaptDeltaQuantile)

@@ -8,8 +8,7 @@
 #include <vector>
 
 #include "../../include/walnuts_cuda.h"
-#include "wn_package.cuh"
-#include "wn_walnutspy.cuh"
+#include "wn_dispatch.cuh"
 
 using namespace wn;
 
@@ -34,6 +33,8 @@ struct wn_handle {
   int warmup_iter = 0, adaptH = 0, adaptDelta = 0;
   bool adapt_exported = false;
   double adHtarget = 0.8, adTarget = 0.6, adQuant = 0.9;
+  int maxFPiter = 30;                       // integratorAuxPar defaults, adaptiveIntegrators.py:37
+  double FPtol = 1.0e-8, gradThresh = 5.0;
   int64_t n_p0 = 0, n_p1 = 0;
   double tau = 1.0;
   double inv_var_max = 1.0;
@@ -56,134 +57,11 @@ static int fail(wn_handle* h, int code, const std::string& msg) {
       return fail(h, WN_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));      \
   } while (0)
 
-// ------------------------------------------------------------------------------------------
-// kernel dispatch
-// ------------------------------------------------------------------------------------------
-template <int G, int E2>
-using StdNormalT = DiagGaussT<G, E2, true>;
-template <int G, int E2>
-using DiagT = DiagGaussT<G, E2, false>;
-
-struct LaunchPlan {
-  const void* fn;
-  int G, E2, NT;
-  size_t smem;
-  bool package;
-};
-
-template <template <int, int> class T, int G, int E2, int NT, int MINB = 1, bool ADAPT = false>
-static LaunchPlan plan_wpy() {
-  LaunchPlan p;
-  p.fn = (const void*)walnutspy_kernel<T, G, E2, NT, MINB, ADAPT>;
-  p.G = G; p.E2 = E2; p.NT = NT;
-  p.smem = (size_t)(3 * 2 * E2 * NT + 2 * ((G + 31) / 32) * 8 + T<G, E2>::smem_doubles(NT)) * sizeof(double);
-  p.package = false;
-  return p;
-}
-template <template <int, int> class T, int G, int E2, int NT>
-static LaunchPlan plan_pkg() {
-  LaunchPlan p;
-  p.fn = (const void*)package_kernel<T, G, E2, NT>;
-  p.G = G; p.E2 = E2; p.NT = NT;
-  p.smem = (size_t)(3 * 2 * E2 * NT + 2 * ((G + 31) / 32) * 8 + T<G, E2>::smem_doubles(NT)) * sizeof(double);
-  p.package = true;
-  return p;
-}
-
-// mode: 0 = WALNUTSpy kernel, 1 = package kernel, 2 = WALNUTSpy kernel with warm-up adaptation
-template <template <int, int> class T, int G, int E2, int NT>
-static LaunchPlan plan_for(int mode) {
-  if (mode == 1) return plan_pkg<T, G, E2, NT>();
-  if (mode == 2) return plan_wpy<T, G, E2, NT, 1, true>();
-  return plan_wpy<T, G, E2, NT>();
-}
-
-template <template <int, int> class T>
-static bool pick_generic(int pkg, int d, LaunchPlan& p) {
-#define WN_PICK(G, E2, NT)                                              \
-  if (d <= 2 * (G) * (E2)) {                                            \
-    p = plan_for<T, G, E2, NT>(pkg);                                    \
-    return true;                                                        \
-  }
-  WN_PICK(1, 2, 128)
-  WN_PICK(1, 6, 128)
-  WN_PICK(4, 4, 128)
-  WN_PICK(16, 4, 128)
-  WN_PICK(32, 8, 128)
-  WN_PICK(64, 8, 64)
-  WN_PICK(256, 4, 256)
-#undef WN_PICK
-  return false;
-}
-template <template <int, int> class T>
-static bool pick_warp(int pkg, int d, LaunchPlan& p) {  // targets that need the chain inside one warp
-#define WN_PICK(G, E2, NT)                                              \
-  if (d <= 2 * (G) * (E2)) {                                            \
-    p = plan_for<T, G, E2, NT>(pkg);                                    \
-    return true;                                                        \
-  }
-  WN_PICK(1, 6, 128)
-  WN_PICK(4, 4, 128)
-  WN_PICK(16, 4, 128)
-  WN_PICK(32, 8, 128)
-#undef WN_PICK
-  return false;
-}
-
+// kernel dispatch: wn_dispatch.cuh; one translation unit per kernel family (plans_*.cu) so they compile in parallel
 static bool pick_plan(const wn_config& c, bool adapt, LaunchPlan& p) {
-  const int pkg = (c.mode == WN_MODE_PACKAGE) ? 1 : (adapt ? 2 : 0);
-  switch (c.target) {
-    case WN_TARGET_STD_NORMAL: return pick_generic<StdNormalT>(pkg, c.d, p);
-    case WN_TARGET_DIAG_GAUSS: {
-      if (pkg == 0 && c.d > 512 && c.d <= 1024) {
-        // BASELINE config 2 (d = 1000): 128 threads x 8 coordinates, 4 blocks / SM (128 registers);
-        // WN_VARIANT selects the alternatives measured in DESIGN.md section 6 (tuning only)
-        const char* v = getenv("WN_VARIANT");
-        switch (v ? atoi(v) : 0) {
-          case 1: p = plan_wpy<DiagT, 64, 8, 64, 1>(); return true;
-          case 2: p = plan_wpy<DiagT, 128, 4, 128, 3>(); return true;
-          default: p = plan_wpy<DiagT, 128, 4, 128, 4>(); return true;
-        }
-      }
-      return pick_generic<DiagT>(pkg, c.d, p);
-    }
-    case WN_TARGET_FUNNEL:
-      if (pkg == 0 && c.d <= 12) {   // BASELINE config 3 (funnel10): one thread per chain
-        const char* v = getenv("WN_VARIANT");
-        if (v && atoi(v) == 1) p = plan_wpy<FunnelT, 1, 6, 128, 3>();
-        else p = plan_wpy<FunnelT, 1, 6, 128, 1>();
-        return true;
-      }
-      return pick_warp<FunnelT>(pkg, c.d, p);
-    case WN_TARGET_FUNNEL_PKG: return pick_warp<FunnelPkgT>(pkg, c.d, p);
-    case WN_TARGET_LOGREG: {
-      if (c.d > 128) return false;
-      // block-cooperative gradient (8 chains per CTA share every load of X) for the plain WALNUTSpy kernel;
-      // the per-warp version serves package mode / warm-up adaptation and WN_VARIANT=1 (comparison)
-      const char* v = getenv("WN_VARIANT");
-      if (pkg == 0 && c.integrator != WN_INT_YOSHIDA && !(v && atoi(v) == 1)) p = plan_wpy<LogRegCoopT, 32, 2, 256>();
-      else p = plan_for<LogRegT, 32, 2, 256>(pkg);
-      return true;
-    }
-    case WN_TARGET_STOCK_WATSON: {
-      // d = 3T; thread t owns B consecutive time steps: T <= G*B
-      if (c.d % 3 != 0) return false;
-      const int T = c.d / 3;
-      if (T <= 64 * 4) {
-        // 6 blocks / SM (168 registers, 12 warps) measured 9 % faster than 4 blocks at 255 registers
-        if (pkg == 0) p = plan_wpy<StockWatsonT, 64, 7, 64, 6>();
-        else p = plan_for<StockWatsonT, 64, 7, 64>(pkg);
-        return true;
-      }
-      if (T <= 128 * 4) { p = plan_for<StockWatsonT, 128, 7, 128>(pkg); return true; }
-      return false;
-    }
-    case WN_TARGET_CORR_GAUSS:
-      if (c.d != 2) return false;
-      p = plan_for<CorrGaussT, 1, 1, 128>(pkg);
-      return true;
-    default: return false;
-  }
+  if (c.mode == WN_MODE_PACKAGE) return wn_pick_plan_pkg(c, p);
+  if (c.integrator > WN_INT_YOSHIDA) return wn_pick_plan_ext(c, p);
+  return adapt ? wn_pick_plan_adapt(c, p) : wn_pick_plan_wpy(c, p);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -264,7 +142,7 @@ int wn_create(const wn_config* cfg, wn_handle** out) {
   if (!(c.delta > 0)) return fail(h, WN_EINVAL, "non-positive max_error");
   if (c.mode != WN_MODE_WALNUTSPY && c.mode != WN_MODE_PACKAGE) return fail(h, WN_EINVAL, "bad mode");
   if (c.mode == WN_MODE_WALNUTSPY) {
-    if (c.integrator < WN_INT_FIXED || c.integrator > WN_INT_YOSHIDA) return fail(h, WN_EINVAL, "bad integrator");
+    if (c.integrator < WN_INT_FIXED || c.integrator > WN_INT_RESCALED) return fail(h, WN_EINVAL, "bad integrator");
     if (c.minC < 0 || c.maxC < c.minC || c.maxC > 30) return fail(h, WN_EINVAL, "need 0 <= minC <= maxC <= 30");
     if (!(c.jitter >= 0 && c.jitter < 1)) return fail(h, WN_EINVAL, "stepSizeRandScale must be in [0,1)");
   }
@@ -357,6 +235,18 @@ int wn_set_data(wn_handle* h, const char* key, const double* ptr, int64_t n, int
     return WN_OK;
   }
   return fail(h, WN_EINVAL, std::string("unknown data key ") + key);
+}
+
+int wn_set_aux(wn_handle* h, const char* key, double value) {
+  if (!h || !key) return fail(h, WN_EINVAL, "wn_set_aux: bad argument");
+  if (!strcmp(key, "maxFPiter")) {
+    if (!(value >= 0 && value <= 1e6)) return fail(h, WN_EINVAL, "bad maxFPiter");
+    h->maxFPiter = (int)value;
+    return WN_OK;
+  }
+  if (!strcmp(key, "FPtol")) { h->FPtol = value; return WN_OK; }
+  if (!strcmp(key, "rescaledGradThresh")) { h->gradThresh = value; return WN_OK; }
+  return fail(h, WN_EINVAL, std::string("unknown aux key ") + key);
 }
 
 int wn_set_adapt(wn_handle* h, int64_t warmup_iter, int adaptH, double adaptHtarget, int adaptDelta,
@@ -493,6 +383,7 @@ static int run_async_impl(wn_handle* h, int64_t n_iter, double* d_draws, double*
     P.warmup_iter = h->warmup_iter; P.adaptH = h->adaptH; P.adaptDelta = h->adaptDelta;
     P.p2prob = 1.0 - h->adHtarget; P.adTarget = h->adTarget; P.adQuant = h->adQuant;
     P.adapt_state = h->d_adapt_state; P.adapt_hist = h->d_adapt_hist;
+    P.maxFPiter = h->maxFPiter; P.FPtol = h->FPtol; P.gradThresh = h->gradThresh;
     // once adaptation has run, the adapted per-chain H / delta are the step sizes (WALNUTS.py:137,144)
     P.Hstep = h->d_H; P.delta = h->d_delta; P.state = h->d_state; P.draws = d_draws; P.diag = d_diag;
     P.orbit_min = d_omin; P.orbit_max = d_omax;

@@ -1,0 +1,4 @@
+// Kernel family "ext": see wn_dispatch.cuh.
+#include "wn_dispatch.cuh"
+
+bool wn_pick_plan_ext(const wn_config& c, wn::LaunchPlan& p) { return wn::pick_plan_family<wn::FAM_EXT>(c, p); }

@@ -110,6 +110,39 @@ struct Group {
     }
   }
 
+  // NaN-propagating maximum (numpy's np.max) over the group, same protocol as sum()
+  __device__ __forceinline__ static double maxn2(double a, double b) { return (b > a || b != b) ? b : a; }
+  template <int NV>
+  __device__ __forceinline__ static void maxn(double (&x)[NV], double* red, int& parity) {
+    if constexpr (G == 1) {
+      return;
+    } else {
+      const unsigned m = mask();
+#pragma unroll
+      for (int off = LANES / 2; off >= 1; off >>= 1) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) x[k] = maxn2(x[k], __shfl_xor_sync(m, x[k], off));
+      }
+      if constexpr (G > 32) {
+        const int w = threadIdx.x >> 5;
+        double* buf = red + parity * (WARPS * NV);
+        if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+          for (int k = 0; k < NV; ++k) buf[w * NV + k] = x[k];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+          double s = buf[k];
+#pragma unroll
+          for (int ww = 1; ww < WARPS; ++ww) s = maxn2(s, buf[ww * NV + k]);
+          x[k] = s;
+        }
+        parity ^= 1;
+      }
+    }
+  }
+
   // broadcast a value chosen by thread 0 of the group (used for queue grabs)
   __device__ __forceinline__ static uint32_t bcast0(uint32_t v, uint32_t* sh) {
     if constexpr (G == 1) {

@@ -1,0 +1,153 @@
+// Kernel dispatch by (kernel family, target, dimension).  Each family -- plain WALNUTSpy transition, package
+// transition, WALNUTSpy with warm-up adaptation, extended integrators -- is instantiated in its own
+// translation unit (plans_*.cu) so that the families compile in parallel; capi.cu only sees the four
+// wn_pick_plan_* entry points.
+#pragma once
+#include <cstdlib>
+
+#include "../../include/walnuts_cuda.h"
+#include "wn_package.cuh"
+#include "wn_walnutspy.cuh"
+
+namespace wn {
+
+struct LaunchPlan {
+  const void* fn;
+  int G, E2, NT;
+  size_t smem;
+  bool package;
+};
+
+enum { FAM_WPY = 0, FAM_PKG = 1, FAM_ADAPT = 2, FAM_EXT = 3 };
+
+template <int G, int E2>
+using StdNormalT = DiagGaussT<G, E2, true>;
+template <int G, int E2>
+using DiagT = DiagGaussT<G, E2, false>;
+
+template <template <int, int> class T, int G, int E2, int NT, int MINB = 1, bool ADAPT = false, bool EXT = false>
+static LaunchPlan plan_wpy() {
+  LaunchPlan p;
+  p.fn = (const void*)walnutspy_kernel<T, G, E2, NT, MINB, ADAPT, EXT>;
+  p.G = G; p.E2 = E2; p.NT = NT;
+  p.smem = (size_t)(3 * 2 * E2 * NT + 2 * ((G + 31) / 32) * 8 + T<G, E2>::smem_doubles(NT)) * sizeof(double);
+  p.package = false;
+  return p;
+}
+template <template <int, int> class T, int G, int E2, int NT>
+static LaunchPlan plan_pkg() {
+  LaunchPlan p;
+  p.fn = (const void*)package_kernel<T, G, E2, NT>;
+  p.G = G; p.E2 = E2; p.NT = NT;
+  p.smem = (size_t)(3 * 2 * E2 * NT + 2 * ((G + 31) / 32) * 8 + T<G, E2>::smem_doubles(NT)) * sizeof(double);
+  p.package = true;
+  return p;
+}
+
+template <int FAM, template <int, int> class T, int G, int E2, int NT>
+static LaunchPlan plan_for() {
+  if constexpr (FAM == FAM_PKG) return plan_pkg<T, G, E2, NT>();
+  else if constexpr (FAM == FAM_ADAPT) return plan_wpy<T, G, E2, NT, 1, true>();
+  else if constexpr (FAM == FAM_EXT) return plan_wpy<T, G, E2, NT, 1, true, true>();
+  else return plan_wpy<T, G, E2, NT>();
+}
+
+#define WN_PICK(G, E2, NT)                                              \
+  if (d <= 2 * (G) * (E2)) {                                            \
+    p = plan_for<FAM, T, G, E2, NT>();                                  \
+    return true;                                                        \
+  }
+template <int FAM, template <int, int> class T>
+static bool pick_generic(int d, LaunchPlan& p) {
+  WN_PICK(1, 2, 128)
+  WN_PICK(1, 6, 128)
+  WN_PICK(4, 4, 128)
+  WN_PICK(16, 4, 128)
+  WN_PICK(32, 8, 128)
+  WN_PICK(64, 8, 64)
+  WN_PICK(256, 4, 256)
+  return false;
+}
+template <int FAM, template <int, int> class T>
+static bool pick_warp(int d, LaunchPlan& p) {  // targets that need the chain inside one warp
+  WN_PICK(1, 6, 128)
+  WN_PICK(4, 4, 128)
+  WN_PICK(16, 4, 128)
+  WN_PICK(32, 8, 128)
+  return false;
+}
+#undef WN_PICK
+
+template <int FAM>
+static bool pick_plan_family(const wn_config& c, LaunchPlan& p) {
+  switch (c.target) {
+    case WN_TARGET_STD_NORMAL: return pick_generic<FAM, StdNormalT>(c.d, p);
+    case WN_TARGET_DIAG_GAUSS: {
+      if constexpr (FAM == FAM_WPY) {
+        if (c.d > 512 && c.d <= 1024) {
+          // BASELINE config 2 (d = 1000): 128 threads x 8 coordinates, 4 blocks / SM (128 registers);
+          // WN_VARIANT selects the alternatives measured in DESIGN.md section 6 (tuning only)
+          const char* v = getenv("WN_VARIANT");
+          switch (v ? atoi(v) : 0) {
+            case 1: p = plan_wpy<DiagT, 64, 8, 64, 1>(); return true;
+            case 2: p = plan_wpy<DiagT, 128, 4, 128, 3>(); return true;
+            default: p = plan_wpy<DiagT, 128, 4, 128, 4>(); return true;
+          }
+        }
+      }
+      return pick_generic<FAM, DiagT>(c.d, p);
+    }
+    case WN_TARGET_FUNNEL:
+      if constexpr (FAM == FAM_WPY) {
+        if (c.d <= 12) {   // BASELINE config 3 (funnel10): one thread per chain
+          const char* v = getenv("WN_VARIANT");
+          if (v && atoi(v) == 1) p = plan_wpy<FunnelT, 1, 6, 128, 3>();
+          else p = plan_wpy<FunnelT, 1, 6, 128, 1>();
+          return true;
+        }
+      }
+      return pick_warp<FAM, FunnelT>(c.d, p);
+    case WN_TARGET_FUNNEL_PKG: return pick_warp<FAM, FunnelPkgT>(c.d, p);
+    case WN_TARGET_LOGREG: {
+      if (c.d > 128) return false;
+      // block-cooperative gradient (8 chains per CTA share every load of X) for the plain WALNUTSpy kernel;
+      // the per-warp version serves package mode / warm-up adaptation / the other integrators and
+      // WN_VARIANT=1 (comparison)
+      if constexpr (FAM == FAM_WPY) {
+        const char* v = getenv("WN_VARIANT");
+        if (c.integrator != WN_INT_YOSHIDA && !(v && atoi(v) == 1)) {
+          p = plan_wpy<LogRegCoopT, 32, 2, 256>();
+          return true;
+        }
+      }
+      p = plan_for<FAM, LogRegT, 32, 2, 256>();
+      return true;
+    }
+    case WN_TARGET_STOCK_WATSON: {
+      // d = 3T; thread t owns B consecutive time steps: T <= G*B
+      if (c.d % 3 != 0) return false;
+      const int T = c.d / 3;
+      if (T <= 64 * 4) {
+        // 6 blocks / SM (168 registers, 12 warps) measured 9 % faster than 4 blocks at 255 registers
+        if constexpr (FAM == FAM_WPY) p = plan_wpy<StockWatsonT, 64, 7, 64, 6>();
+        else p = plan_for<FAM, StockWatsonT, 64, 7, 64>();
+        return true;
+      }
+      if (T <= 128 * 4) { p = plan_for<FAM, StockWatsonT, 128, 7, 128>(); return true; }
+      return false;
+    }
+    case WN_TARGET_CORR_GAUSS:
+      if (c.d != 2) return false;
+      p = plan_for<FAM, CorrGaussT, 1, 1, 128>();
+      return true;
+    default: return false;
+  }
+}
+
+}  // namespace wn
+
+// one definition per translation unit plans_{wpy,pkg,adapt,ext}.cu
+bool wn_pick_plan_wpy(const wn_config& c, wn::LaunchPlan& p);
+bool wn_pick_plan_pkg(const wn_config& c, wn::LaunchPlan& p);
+bool wn_pick_plan_adapt(const wn_config& c, wn::LaunchPlan& p);
+bool wn_pick_plan_ext(const wn_config& c, wn::LaunchPlan& p);

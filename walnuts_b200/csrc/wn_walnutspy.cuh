@@ -49,10 +49,16 @@ struct RunParams {
   double p2prob, adTarget, adQuant;
   double* adapt_state;   // [n_chains, WN_ADAPT_STRIDE]: H, delta, npush, q[5], n[5], hasNaN, nhist
   double* adapt_hist;    // [n_chains, warmup_iter]: sorted history of orbitEnergyError / delta
+  // integratorAuxPar fields of the extended integrators (adaptiveIntegrators.py:36-44); EXT kernels only
+  int maxFPiter;
+  double FPtol, gradThresh;
 };
 #define WN_ADAPT_STRIDE 16
 
 enum { KIND_FIXED = 0, KIND_D = 1, KIND_R2P = 2, KIND_YOSHIDA = 3 };   // 3: adaptYoshidaD (adaptiveIntegrators.py:142-240)
+// EXT kernels: adaptLeapFrogFlowD (:246-356), adaptImplicitMidpointD (:478-641, fixed-point variant),
+// adaptRescaledLeapFrogD (:660-762)
+enum { KIND_FLOW = 4, KIND_MIDPOINT = 5, KIND_RESCALED = 6 };
 #define WN_Y_FIRSTLAST 1.351207191959658
 #define WN_Y_MIDDLE (-1.702414383919315)
 enum { PH_FWD = 0, PH_REDO = 1, PH_BWD = 2, PH_INIT = 3 };
@@ -85,8 +91,9 @@ struct Ctl {
   double p2q[5], igr, maxd, Hprev;
 };
 
-template <template <int, int> class TargetTT, int G, int E2, int NT, int MINB = 1, bool ADAPT = false>
+template <template <int, int> class TargetTT, int G, int E2, int NT, int MINB = 1, bool ADAPT = false, bool EXT = false>
 __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_constant__ RunParams P) {
+  static_assert(!EXT || ADAPT, "EXT kernels are built with the adaptation code (inactive without wn_set_adapt)");
   constexpr int E = 2 * E2;
   constexpr int GPB = NT / G;  // groups per block
   static_assert(NT % G == 0 && (G <= 32 || NT == G), "block must hold whole groups");
@@ -377,7 +384,7 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
         if (--steps_left != 0u) continue;
         st = ST_PASS_END;
       }
-    } else if (st == ST_RUN) {
+    } else if (!EXT && st == ST_RUN) {
       if (yoshida) {
         // one leapfrog of the 4th-order triple (coefficients firstLast, middle, firstLast, :157-173); the
         // energy (Hams[i], :175) and its finiteness only count after the third
@@ -830,7 +837,7 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
       if (t == 0) {
         if (P.nevalF) P.nevalF[cidx] = cf;
         if (P.nevalB) P.nevalB[cidx] = cbk;
-        if constexpr (ADAPT) {
+        if constexpr (ADAPT) if (!EXT || P.adapt_state) {
           double* as = P.adapt_state + (size_t)cidx * WN_ADAPT_STRIDE;
           as[0] = C.Hbig; as[1] = C.delta; as[2] = (double)C.p2npush;
 #pragma unroll
@@ -860,6 +867,7 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
       C.Hbig = P.Hstep ? P.Hstep[cidx] : P.H0;
       C.delta = P.delta ? P.delta[cidx] : P.delta0;
       if constexpr (ADAPT) {
+        if (!EXT || P.adapt_state) {
         const double* as = P.adapt_state + (size_t)cidx * WN_ADAPT_STRIDE;
         C.Hbig = as[0];
         C.delta = as[1];
@@ -868,6 +876,7 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
         for (int i = 0; i < 5; ++i) { C.p2q[i] = as[3 + i]; C.p2n[i] = (int)as[8 + i]; }
         C.adNaN = (int)as[13];
         C.adNhist = (int)as[14];
+        }
       }
       C.it = 0;
       C.chainF = 0;
@@ -884,7 +893,7 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
         C.jlo = __dmul_rn(Hbig, __dadd_rn(1.0, -P.jitter));   // WALNUTS.py:298
         C.jhi = __dmul_rn(Hbig, __dadd_rn(1.0, P.jitter));
       }
-      if constexpr (ADAPT) C.warm = (key.iter <= (uint32_t)P.warmup_iter) ? 1 : 0;   // :209
+      if constexpr (ADAPT) C.warm = ((!EXT || P.adapt_state) && key.iter <= (uint32_t)P.warmup_iter) ? 1 : 0;   // :209
       uint32_t dirbits = 0;
       for (int k = 0; k < P.M; ++k) {
         const double u = rng_uniform(key, STREAM_DIR, (uint32_t)k);   // B = floor(U(0,2)), :216
@@ -1018,6 +1027,267 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
       C.h = h;
       const double Ham0 = C.side ? C.endH1 : C.endH0;
       C.Ham0 = Ham0;
+      if constexpr (EXT) {
+        // ---- extended integrators: the whole macro step runs here (simple loops, group reductions); the
+        // driver above / below is shared.  Registers hold S = (q, vv = xi v, g).  Not a tuned path. ----
+        const double delta = C.delta;
+        const int maxC = P.maxC;
+        const double NaN = __longlong_as_double(0x7ff8000000000000ll);
+        unsigned long long nF = 0, nB = 0;
+        int If = maxC, Ib = maxC;
+        double HO = 0.0, lwt = 0.0, igr = 1.0;
+        save_ck();   // S
+        if (P.kind == KIND_FLOW) {
+          // one attempt, adaptiveIntegrators.py:252-287 / :309-339; returns through the references
+          auto flow_pass = [&](int c, double Href, double& Hl, bool& ok, double& maxErr, double& maxd, double& hh_) {
+            const uint32_t nstep = 1u << c;
+            hh_ = ldexp(h, -c);
+            const double ha_ = 0.5 * hh_, h8 = hh_ / 8.0, h6 = hh_ / 6.0, h2_ = hh_ * hh_;
+            double Hprev = Href;
+            ok = true; maxd = 0.0; maxErr = 0.0;
+            for (uint32_t i = 0; i < nstep; ++i) {
+              double qo[E], go[E], vo[E], gm[E], qm[E];
+#pragma unroll
+              for (int e = 0; e < E; ++e) {
+                qo[e] = q[e]; go[e] = g[e]; vo[e] = v[e];
+                v[e] = fma(ha_, g[e], v[e]);
+                q[e] = fma(hh_, v[e], q[e]);
+              }
+              const double lpp = target.lp_grad(q, g, red, parity);
+              double ke = 0.0;
+#pragma unroll
+              for (int e = 0; e < E; ++e) {
+                v[e] = fma(ha_, g[e], v[e]);
+                ke = fma(v[e], v[e], ke);
+                qm[e] = 0.5 * (q[e] + qo[e]) + h8 * (vo[e] - v[e]);                  // :265
+              }
+              (void)target.lp_grad(qm, gm, red, parity);                            // :266
+              double er[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+              for (int e = 0; e < E; ++e) {
+                const double qf = qo[e] + hh_ * vo[e] + h2_ * ((1.0 / 6.0) * go[e] + (1.0 / 3.0) * gm[e]);   // :269
+                const double sg = h6 * (go[e] + g[e] + 4.0 * gm[e]);
+                const double vf = vo[e] + sg;                                        // :272
+                const double qb = q[e] - hh_ * v[e] + h2_ * ((1.0 / 6.0) * g[e] + (1.0 / 3.0) * gm[e]);     // :275
+                const double vb = -(-v[e] + sg);                                     // :278
+                er[0] = Grp::maxn2(er[0], fabs(qf - q[e]));
+                er[1] = Grp::maxn2(er[1], fabs(vf - v[e]));
+                er[2] = Grp::maxn2(er[2], fabs(qb - qo[e]));
+                er[3] = Grp::maxn2(er[3], fabs(vb - vo[e]));
+              }
+              Grp::template maxn<4>(er, red, parity);
+              double err = er[0];                        // Python max(): a NaN in the first operand sticks
+              err = (er[1] > err) ? er[1] : err;
+              err = (er[2] > err) ? er[2] : err;
+              err = (er[3] > err) ? er[3] : err;
+              maxErr = (i == 0) ? err : Grp::maxn2(maxErr, err);                     // np.max(Errs)
+              double x[1] = {fma(0.5, ke, -lpp)};
+              Grp::template sum<1>(x, red, parity);
+              ok = ok && finite_d(x[0]);
+              maxd = Grp::maxn2(maxd, fabs(x[0] - Hprev));
+              Hprev = x[0];
+            }
+            Hl = Hprev;
+          };
+          double Hl = 0, maxErr = 0, maxd = 0, hhl = 0;
+          bool ok = false;
+          for (int c = 0; c <= maxC; ++c) {              // :250-287 (starts at 0, not minC)
+            if (c > 0) load_ck(1.0);
+            flow_pass(c, Ham0, Hl, ok, maxErr, maxd, hhl);
+            nF += 2ull << c;
+            if (ok && maxErr < delta) { If = c; break; }
+          }
+          HO = Hl;
+          igr = (maxd > 0.0 || maxd != maxd) ? hhl * pow(maxd, -1.0 / 3.0) : INFINITY;   // :294
+          Ib = If;
+          if (If > 0) {                                  // :300-345
+            save_ck();   // O replaces S
+            for (int c = 0; c < If; ++c) {
+              load_ck(-1.0);
+              double Hb, eb, mb, hb; bool okb;
+              flow_pass(c, HO, Hb, okb, eb, mb, hb);
+              nB += 2ull << c;
+              if (okb && eb < delta) { Ib = c; break; }
+            }
+            load_ck(1.0);
+          }
+          lwt = (If != Ib) ? WN_LOG_ZERO : 0.0;
+        } else if (P.kind == KIND_MIDPOINT) {
+          // one attempt with fixed-point iterations, adaptiveIntegrators.py:483-541 / :572-626
+          auto mid_pass = [&](int c, double Href, double& Hl, bool& ok, bool& full, bool& conv, double& maxd,
+                              double& hh_, unsigned long long& nev) {
+            const uint32_t nstep = 1u << c;
+            hh_ = ldexp(h, -c);
+            const double hh2 = 0.5 * hh_ * hh_;
+            double Hprev = Href;
+            ok = finite_d(Href); maxd = 0.0; conv = false;
+            uint32_t done = 0;
+            for (uint32_t i = 0; i < nstep; ++i) {
+              double qt[E], gm[E], mp[E];
+#pragma unroll
+              for (int e = 0; e < E; ++e) qt[e] = q[e] + hh_ * (v[e] + 0.5 * hh_ * g[e]);   // :494
+              conv = false;
+              double oldErr = 1.0e100;
+              for (int it = 0; it < P.maxFPiter; ++it) {                                   // :500-523
+#pragma unroll
+                for (int e = 0; e < E; ++e) mp[e] = 0.5 * (qt[e] + q[e]);
+                (void)target.lp_grad(mp, gm, red, parity);
+                ++nev;
+                double er[1] = {0.0};
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                  const double qn = q[e] + hh_ * v[e] + hh2 * gm[e];
+                  er[0] = Grp::maxn2(er[0], fabs(qn - qt[e]));
+                  qt[e] = qn;
+                }
+                Grp::template maxn<1>(er, red, parity);
+                if (er[0] < P.FPtol) { conv = true; break; }
+                if (er[0] > 1.1 * oldErr) break;
+                oldErr = er[0];
+              }
+              if (!conv) break;                                                            // :525-527
+#pragma unroll
+              for (int e = 0; e < E; ++e) mp[e] = 0.5 * (qt[e] + q[e]);                     // :530
+              (void)target.lp_grad(mp, gm, red, parity);
+              ++nev;
+#pragma unroll
+              for (int e = 0; e < E; ++e) {
+                q[e] = q[e] + hh_ * v[e] + hh2 * gm[e];                                    // :534
+                v[e] = fma(hh_, gm[e], v[e]);                                              // :535
+              }
+              const double lpp = target.lp_grad(q, g, red, parity);                        // :537
+              ++nev;
+              double ke = 0.0;
+#pragma unroll
+              for (int e = 0; e < E; ++e) ke = fma(v[e], v[e], ke);
+              double x[1] = {fma(0.5, ke, -lpp)};
+              Grp::template sum<1>(x, red, parity);
+              ok = ok && finite_d(x[0]);
+              maxd = Grp::maxn2(maxd, fabs(x[0] - Hprev));
+              Hprev = x[0];
+              ++done;
+            }
+            full = (done == nstep);
+            if (!full) {                     // Hams of the missing steps are 0 (:490)
+              maxd = Grp::maxn2(maxd, fabs(0.0 - Hprev));
+              Hprev = 0.0;
+            }
+            Hl = Hprev;
+          };
+          double Hl = 0, maxd = 0, hhl = 0;
+          bool ok = false, full = false, conv = false;
+          for (int c = 0; c <= maxC; ++c) {              // :482-545
+            if (c > 0) load_ck(1.0);
+            mid_pass(c, Ham0, Hl, ok, full, conv, maxd, hhl, nF);
+            if (ok && fabs(Ham0 - Hl) < delta && full) { If = c; break; }
+          }
+          if (!conv) {
+            // the reference ends the process here (sys.exit, :548-550); per-chain failure instead: NaN energy
+            // -> forced reject, stop code 999
+            HO = NaN; Ib = If; lwt = 0.0; igr = NaN;
+          } else {
+            HO = Hl;                                     // :569 (the same expression as Hams[-1])
+            igr = (maxd > 0.0 || maxd != maxd) ? hhl * pow(maxd, -1.0 / 3.0) : INFINITY;   // :561
+            Ib = maxC;                                   // :564
+            save_ck();   // O replaces S
+            for (int c = 0; c <= maxC; ++c) {            // :570-633: the full range
+              load_ck(-1.0);
+              double Hb, mb, hb; bool okb, fullb, convb;
+              mid_pass(c, HO, Hb, okb, fullb, convb, mb, hb, nB);
+              if (okb && fabs(HO - Hb) < delta && fullb) { Ib = c; break; }
+            }
+            load_ck(1.0);
+            lwt = (If != Ib) ? WN_LOG_ZERO : 0.0;
+          }
+        } else {
+          // adaptRescaledLeapFrogD, adaptiveIntegrators.py:660-762: one leapfrog step in coordinates rescaled
+          // per dimension by Sd = 2^-Sred; from the state in the checkpoint with velocity sign `vs`
+          int sred[E], sfw[E];
+          double gbm[E];
+          auto attempt = [&](double vs, double& Ham1) {
+            load_ck(vs);
+            const double hah = 0.5 * h;
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+              const double Sd = ldexp(1.0, -sred[e]);
+              const double qb = q[e] / Sd, gb = Sd * g[e];                                  // :672-673
+              v[e] = fma(hah, gb, v[e]);                                                    // :674
+              q[e] = (qb + h * v[e]) * Sd;                                                  // :675-676
+              gbm[e] = fabs(gb);
+            }
+            const double lpp = target.lp_grad(q, g, red, parity);                           // :677
+            double ke = 0.0;
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+              const double gb1 = ldexp(1.0, -sred[e]) * g[e];                               // :679
+              v[e] = fma(hah, gb1, v[e]);                                                   // :680
+              gbm[e] = 0.5 * (gbm[e] + fabs(gb1));                                          // :681
+              ke = fma(v[e], v[e], ke);
+            }
+            double x[1] = {fma(0.5, ke, -lpp)};
+            Grp::template sum<1>(x, red, parity);
+            Ham1 = x[0];
+          };
+          // :687-697: returns true when the attempt is accepted, otherwise updates sred
+          auto judge = [&](double Href, double Ham1) -> bool {
+            double x[1] = {0.0};
+#pragma unroll
+            for (int e = 0; e < E; ++e) x[0] += (gbm[e] > P.gradThresh) ? 1.0 : 0.0;
+            Grp::template sum<1>(x, red, parity);
+            if (!finite_d(Ham1)) {
+#pragma unroll
+              for (int e = 0; e < E; ++e) sred[e] += 1;
+            } else if (x[0] != 0.0) {
+#pragma unroll
+              for (int e = 0; e < E; ++e) sred[e] += (gbm[e] > P.gradThresh) ? 1 : 0;
+            } else if (fabs(Href - Ham1) > delta) {
+#pragma unroll
+              for (int e = 0; e < E; ++e) sred[e] += 1;
+            } else {
+              return true;
+            }
+            return false;
+          };
+          auto same = [&]() -> bool {
+            double x[1] = {0.0};
+#pragma unroll
+            for (int e = 0; e < E; ++e) x[0] += (sred[e] != sfw[e]) ? 1.0 : 0.0;
+            Grp::template sum<1>(x, red, parity);
+            return x[0] == 0.0;
+          };
+#pragma unroll
+          for (int e = 0; e < E; ++e) sred[e] = 0;
+          double Ham1 = 0.0;
+          for (int c = 0; c <= maxC; ++c) {              // :669-700
+            attempt(1.0, Ham1);
+            ++nF;
+            if (judge(Ham0, Ham1)) { If = c; break; }
+          }
+          HO = Ham1;
+          igr = 1.0;
+#pragma unroll
+          for (int e = 0; e < E; ++e) { sfw[e] = sred[e]; sred[e] = 0; }
+          Ib = If;
+          if (If > 0) {                                  // :718-755
+            save_ck();   // O replaces S
+            for (int c = 0; c <= maxC; ++c) {
+              double Hb;
+              attempt(-1.0, Hb);
+              ++nB;
+              if (judge(HO, Hb)) { Ib = c; break; }
+              if (same()) { Ib = c + 1; break; }
+            }
+            load_ck(1.0);
+          }
+          lwt = same() ? 0.0 : WN_LOG_ZERO;              // :762
+        }
+        C.nF = C.nF + nF;
+        C.nB = C.nB + nB;
+        C.If = If; C.Ib = Ib; C.cSim = If; C.lwt = lwt; C.Hfwd = HO;
+        if constexpr (ADAPT) C.igr = igr;
+        st = ST_LEAF;
+        break;
+      }
       C.phase = PH_FWD;
       const int c0 = (P.kind == KIND_FIXED) ? 0 : P.minC;
       C.c = c0;

@@ -22,12 +22,16 @@ fixedLeapFrog = _Integrator("fixedLeapFrog", 0, "adaptiveIntegrators.py:49-59")
 adaptLeapFrogD = _Integrator("adaptLeapFrogD", 1, "adaptiveIntegrators.py:65-137")
 adaptLeapFrogR2P = _Integrator("adaptLeapFrogR2P", 2, "adaptiveIntegrators.py:361-475")
 adaptYoshidaD = _Integrator("adaptYoshidaD", 3, "adaptiveIntegrators.py:142-240")
+adaptLeapFrogFlowD = _Integrator("adaptLeapFrogFlowD", 4, "adaptiveIntegrators.py:246-356")
+adaptImplicitMidpointD = _Integrator("adaptImplicitMidpointD", 5, "adaptiveIntegrators.py:478-641")
+adaptRescaledLeapFrogD = _Integrator("adaptRescaledLeapFrogD", 6, "adaptiveIntegrators.py:660-762")
+KINDS = {"fixed": 0, "D": 1, "R2P": 2, "Yoshida": 3, "Flow": 4, "Midpoint": 5, "Rescaled": 6}
 
 
 class integratorAuxPar:
-    """adaptiveIntegrators.integratorAuxPar (adaptiveIntegrators.py:36-44); the fields of the
-    integrators that are not on the hot path (maxFPiter, FPtol, FPNewton, rescaledGradThresh) are
-    accepted and ignored."""
+    """adaptiveIntegrators.integratorAuxPar (adaptiveIntegrators.py:36-44).  maxFPiter / FPtol steer
+    adaptImplicitMidpointD, rescaledGradThresh steers adaptRescaledLeapFrogD; FPNewton=True (Newton iterations on
+    the target's Hessian, adaptiveIntegrators.py:503-506) has no CUDA implementation and is refused."""
 
     def __init__(self, minC=0, maxC=10, R2Pprob0=2.0 / 3.0, maxFPiter=30, FPtol=1.0e-8, FPNewton=False,
                  rescaledGradThresh=5.0):

@@ -9,6 +9,7 @@ import math
 import numpy as np
 
 from . import _ffi
+from . import integrators as _ig
 from ._ffi import WalnutsError
 
 
@@ -37,7 +38,7 @@ class ChainBatch:
         cfg = _ffi.WnConfig()
         cfg.target = _ffi.TARGETS[target] if isinstance(target, str) else int(target)
         cfg.mode = {"walnutspy": _ffi.MODE_WALNUTSPY, "package": _ffi.MODE_PACKAGE}[mode]
-        cfg.integrator = {"fixed": 0, "D": 1, "R2P": 2, "Yoshida": 3}[integrator] if isinstance(integrator, str) else int(integrator)
+        cfg.integrator = _ig.KINDS[integrator] if isinstance(integrator, str) else int(integrator)
         cfg.d, cfg.n_chains, cfg.device = int(d), int(n_chains), int(device)
         cfg.dg = int(d if dg is None else dg)
         cfg.M, cfg.minC, cfg.maxC = int(M), int(minC), int(maxC)
@@ -93,6 +94,12 @@ class ChainBatch:
             n = arr.numel()
         p, dev = _ptr(arr)
         self._check(self._lib.wn_set_data(self._h, key.encode(), p, n, dev), f"wn_set_data({key})")
+
+    def set_aux(self, maxFPiter=None, FPtol=None, rescaledGradThresh=None):
+        """integratorAuxPar fields of adaptImplicitMidpointD / adaptRescaledLeapFrogD (adaptiveIntegrators.py:36-44)."""
+        for k, val in (("maxFPiter", maxFPiter), ("FPtol", FPtol), ("rescaledGradThresh", rescaledGradThresh)):
+            if val is not None:
+                self._check(self._lib.wn_set_aux(self._h, k.encode(), float(val)), f"wn_set_aux({k})")
 
     def set_adapt(self, warmup_iter, adaptH=True, adaptHtarget=0.8, adaptDelta=True, adaptDeltaTarget=0.6,
                   adaptDeltaQuantile=0.9):
