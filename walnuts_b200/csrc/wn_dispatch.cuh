@@ -115,8 +115,12 @@ static bool pick_plan_family(const wn_config& c, LaunchPlan& p) {
       // WN_VARIANT=1 (comparison)
       if constexpr (FAM == FAM_WPY) {
         const char* v = getenv("WN_VARIANT");
-        if (c.integrator != WN_INT_YOSHIDA && !(v && atoi(v) == 1)) {
-          p = plan_wpy<LogRegCoopT, 32, 2, 256>();
+        const int var = v ? atoi(v) : 0;
+        if (c.integrator != WN_INT_YOSHIDA && var != 1) {
+          // default: FP64 tensor-core gradient with TMA-staged row tiles; WN_VARIANT=2: the FMA-pipe version
+          if (var == 2 || c.d > 104) p = plan_wpy<LogRegCoopT, 32, 2, 256>();
+          else if (c.d <= 32) p = plan_wpy<LogRegMma32T, 32, 2, 256>();
+          else p = plan_wpy<LogRegMma104T, 32, 2, 256>();
           return true;
         }
       }

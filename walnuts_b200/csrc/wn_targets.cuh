@@ -728,3 +728,314 @@ struct LogRegCoopT {
 };
 
 }  // namespace wn
+
+namespace wn {
+
+// Branch-free double-precision helpers for the sigmoid / log-likelihood of the tensor-core logistic regression
+// (straight-line code lets the compiler interleave them with the DMMA stream).  Accuracy <= 2 ulp (checked against
+// mpmath); NaN propagates.
+__device__ __forceinline__ double exp_nonpos(double x) {   // exp(x) for x <= 0
+  x = (x < -708.0) ? -708.0 : x;                            // below: < 3.4e-308, irrelevant next to 1
+  const double z = fma(x, 1.4426950408889634, 6755399441055744.0);
+  const int k = __double2loint(z);
+  const double t = z - 6755399441055744.0;                  // rint(x log2 e)
+  double r = fma(t, -6.93147180369123816490e-01, x);        // Cody-Waite
+  r = fma(t, -1.90821492927058770002e-10, r);
+  double p = 1.6059043836821613e-10;                        // Taylor to r^13 / 13!: |r| <= 0.347 -> 4e-18
+  p = fma(p, r, 2.08767569878681e-09);
+  p = fma(p, r, 2.505210838544172e-08);
+  p = fma(p, r, 2.755731922398589e-07);
+  p = fma(p, r, 2.7557319223985893e-06);
+  p = fma(p, r, 2.48015873015873e-05);
+  p = fma(p, r, 1.984126984126984e-04);
+  p = fma(p, r, 1.388888888888889e-03);
+  p = fma(p, r, 8.333333333333333e-03);
+  p = fma(p, r, 4.1666666666666664e-02);
+  p = fma(p, r, 1.6666666666666666e-01);
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  return p * __longlong_as_double((long long)(k + 1023) << 52);
+}
+__device__ __forceinline__ double rcp_pos(double d) {       // 1 / d for a positive normal d of moderate size
+  float yf;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(yf) : "f"((float)d));   // MUFU.RCP, no slow path; 2^-22 accurate
+  double y = (double)yf;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const double e = fma(-d, y, 1.0);
+    y = fma(y, e, y);
+  }
+  return y;
+}
+// log1p(z) for 0 <= z <= 1 given inv = 1 / (1 + z):  log(u) + (z - (u - 1)) / u with u = fl(1 + z),
+// log(u) = [u > sqrt 2] ln 2 + 2 atanh(s), s = f / (2 + f), f = m - 1
+__device__ __forceinline__ double log1p_unit(double z, double inv) {
+  const double u = 1.0 + z, c = z - (u - 1.0);
+  const bool big = u > 1.4142135623730951;
+  const double m = big ? 0.5 * u : u;
+  const double f = m - 1.0;
+  const double s = f * rcp_pos(2.0 + f), s2 = s * s;
+  double q = 1.0 / 21.0;
+  q = fma(q, s2, 1.0 / 19.0);
+  q = fma(q, s2, 1.0 / 17.0);
+  q = fma(q, s2, 1.0 / 15.0);
+  q = fma(q, s2, 1.0 / 13.0);
+  q = fma(q, s2, 1.0 / 11.0);
+  q = fma(q, s2, 1.0 / 9.0);
+  q = fma(q, s2, 1.0 / 7.0);
+  q = fma(q, s2, 1.0 / 5.0);
+  q = fma(q, s2, 1.0 / 3.0);
+  q *= s2;
+  const double two_s = 2.0 * s;
+  return (big ? 0.6931471805599453 : 0.0) + fma(two_s, q, two_s) + c * inv;
+}
+
+// ---- T4 on the FP64 tensor cores: block-cooperative gradient with DMMA fragments and TMA-staged row tiles ----------
+// Same protocol as LogRegCoopT (8 chains per CTA of 8 warps, publish -> coop_eval -> collect), different engine:
+//   * the 8 lock-stepped chains of the CTA are the N = 8 dimension of `mma.sync.m8n8k4.f64` (SASS DMMA.8x8x4);
+//   * X is streamed in tiles of 8 rows (8 P doubles, contiguous in row-major X) by per-warp bulk async copies
+//     (`cp.async.bulk`, TMA engine, SASS UBLKCP) into a private 3-stage ring in shared memory, completing on per-stage
+//     mbarriers; the warp that consumes a stage also refills it, so the main loop has no CTA-wide barrier at all;
+//   * phase 1: eta[8 rows x 8 chains] = X_tile[8 x P] beta[P x 8]: beta lives in registers as B fragments for the
+//     whole evaluation (one double per lane per 4 coordinates), A fragments come from the staged tile
+//     (conflict-free: row stride P = 100 doubles puts the 4 rows of a half-warp 8 banks apart); 4 accumulators
+//     break the dependent-DMMA chain;
+//   * r = y - sigmoid(eta) on the C fragment (2 values per lane; branch-free exp / reciprocal / log1p above),
+//     re-laid out as two B fragments by 4 shuffles;
+//   * phase 2: grad[P x 8 chains] += X_tile^T[P x 8 rows] r[8 rows x 8]: A fragments are the transposed read of
+//     the same staged tile (also conflict-free), accumulators stay in registers (2 doubles per lane per 8 coords);
+//   * software pipeline: trip j runs phase 1 of tile j next to sigmoid + phase 2 of tile j - 1 (independent
+//     instruction streams in one basic block; loop bounds are compile-time through PCAP >= P);
+//   * the 8 warps' partial gradients are combined in a fixed order through the (then idle) stage buffers.
+// Per CTA-evaluation X is read once from L2 (80 MB for N = 100 000, P = 100; it fits the 126 MB L2); per 8-row tile
+// a warp issues PCAP/4 + PCAP/4 DMMA (52 for PCAP = 104) against as many shared loads.
+template <int G, int E2, int PCAP>
+struct LogRegMmaTP {
+  static constexpr int E = 2 * E2;
+  static constexpr bool PAIR_LAYOUT = true;
+  static constexpr bool BLOCK_LOCKSTEP = false;
+  static constexpr bool LAZY_ENERGY = false;
+  static constexpr bool COOP = true;
+  static constexpr int NTC = 256, NW = 8, C = 8, PMAX = 128, KS = PCAP / 4, CT = PCAP / 8, RT = 8, S = 3;
+  static constexpr int WSTAGE = S * RT * PCAP;      // doubles of stage ring per warp
+  static_assert(G == 32 && E2 == 2 && PCAP % 8 == 0 && PCAP <= 104, "tensor-core logistic regression: one warp per chain, P <= 104");
+  static_assert(WSTAGE >= CT * 64, "the ring doubles as the reduction buffer");
+  // shared: bs[PMAX][C] | gs[C][PMAX] | lps[NW][C] | act[C] | need[C] | full[NW][4] | ring[NW][WSTAGE] | pad[PMAX]
+  __host__ __device__ static constexpr int smem_doubles(int) {
+    return PMAX * C + C * PMAX + NW * C + 2 * C + NW * 4 + NW * WSTAGE + PMAX;
+  }
+  const double *X, *y;
+  int N, P;
+  double itau2;
+  double *bs, *gs, *lps, *act, *need, *ring;
+  uint64_t* full;
+  __device__ __forceinline__ int coord(int e, int t) const { return coord_of<G>(e, t); }
+  __device__ __forceinline__ void init(const TargetParams& tp, int d, int, double* tsm) {
+    X = tp.p0; y = tp.p1; N = tp.n0; P = d; itau2 = tp.c0;
+    bs = tsm; gs = bs + PMAX * C; lps = gs + C * PMAX; act = lps + NW * C; need = act + C;
+    full = reinterpret_cast<uint64_t*>(need + C);
+    ring = need + C + NW * 4;
+    for (int i = threadIdx.x; i < PMAX * C; i += NTC) bs[i] = 0.0;
+    for (int i = threadIdx.x; i < NW * WSTAGE + PMAX; i += NTC) ring[i] = 0.0;   // stale reads must be finite
+    if (threadIdx.x == 0) {
+      for (int i = 0; i < NW * 4; ++i) mbar_init(&full[i], 1);
+      mbar_fence_init();
+    }
+    __syncthreads();
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __device__ __forceinline__ double lp_grad(const double (&)[E], double (&)[E], double*, int&) const { return 0.0; }
+
+  // see LogRegCoopT::publish
+  __device__ __forceinline__ void publish(const double (&q)[E], bool active, bool need_lp) const {
+    const int w = threadIdx.x >> 5, t = threadIdx.x & 31;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int k = coord_of<G>(e, t);
+      if (k < P) bs[k * C + w] = active ? q[e] : 0.0;
+    }
+    if (t == 0) { act[w] = active ? 1.0 : 0.0; need[w] = (active && need_lp) ? 1.0 : 0.0; }
+  }
+
+  __device__ __forceinline__ static void dmma(double (&c)[2], double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+  }
+
+  // `gt`: number of tiles this warp has consumed so far (kept by the caller across evaluations): tile g lives in
+  // stage g % S of the warp's ring and completes phase (g / S) & 1 of that stage's mbarrier.
+  __device__ __forceinline__ void coop_eval(uint32_t& gt) const {
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    const int lr = lane >> 2, lc = lane & 3;       // fragment coordinates
+    bool any = false, anyneed = false;
+#pragma unroll
+    for (int c = 0; c < C; ++c) { any = any || (act[c] != 0.0); anyneed = anyneed || (need[c] != 0.0); }
+    if (!any) return;
+    const bool nl0 = need[2 * lc] != 0.0, nl1 = need[2 * lc + 1] != 0.0;
+    // beta as B fragments: B[k = 4 kk + lc][n = chain lr]
+    double bf[KS];
+#pragma unroll
+    for (int kk = 0; kk < KS; ++kk) bf[kk] = bs[(4 * kk + lc) * C + lr];      // rows >= P of bs are zero
+    double ga[CT][2];
+#pragma unroll
+    for (int ct = 0; ct < CT; ++ct) ga[ct][0] = ga[ct][1] = 0.0;
+    double lp0 = 0.0, lp1 = 0.0;
+
+    const int ntile = (N + RT - 1) / RT;
+    const int mine = (ntile > w) ? (ntile - w + NW - 1) / NW : 0;     // tiles w, w + NW, ...
+    const int stage_d = RT * P;                                       // doubles per stage
+    double* myring = ring + w * WSTAGE;
+    uint64_t* mybar = full + w * 4;
+    auto issue = [&](int j) {     // lane 0: start the copy of my j-th tile
+      const uint32_t g = gt + (uint32_t)j;
+      const int st_ = (int)(g % (uint32_t)S);
+      const int n0 = (w + j * NW) * RT;
+      const int nrows = min(RT, N - n0);
+      const uint32_t bytes = (uint32_t)(nrows * P * 8);
+      if ((bytes & 15u) == 0u) {
+        mbar_expect_tx(&mybar[st_], bytes);
+        bulk_g2s(myring + st_ * stage_d, X + (size_t)n0 * P, bytes, &mybar[st_]);
+      } else {
+        // ragged last tile whose byte count is not a multiple of 16: plain copy, then complete the phase
+        for (int i = 0; i < nrows * P; ++i) myring[st_ * stage_d + i] = __ldg(X + (size_t)n0 * P + i);
+        mbar_arrive(&mybar[st_]);
+      }
+    };
+    if (lane == 0 && mine > 0) issue(0);
+
+    // software pipeline: trip jj = phase 1 of tile jj  ||  sigmoid + phase 2 of tile jj - 1
+    double ep[2] = {0.0, 0.0};        // eta of the previous tile (C fragment)
+    double yp = 0.0;                  // its y (row lr)
+    bool okp = false;                 // its row lr exists
+    const double* sxp = myring;       // its stage
+    for (int jj = 0; jj <= mine; ++jj) {
+      // stage of tile jj + 1 held tile jj - 2, released by the __syncwarp at the end of the previous trip
+      if (lane == 0 && jj + 1 < mine) issue(jj + 1);
+      double e4[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+      double yn = 0.0;
+      bool okn = false;
+      const double* sxn = myring;
+      if (jj < mine) {
+        const uint32_t g = gt + (uint32_t)jj;
+        sxn = myring + (g % (uint32_t)S) * stage_d;
+        const int n0 = (w + jj * NW) * RT;
+        const int nrows = min(RT, N - n0);
+        okn = lr < nrows;
+        yn = okn ? __ldg(y + n0 + lr) : 0.0;
+        mbar_wait(&mybar[g % (uint32_t)S], (g / (uint32_t)S) & 1u);
+        if (nrows < RT) {            // partial last tile: rows beyond the data must be finite for phase 2
+          for (int i = nrows * P + lane; i < RT * P; i += 32) const_cast<double*>(sxn)[i] = 0.0;
+          __syncwarp();
+        }
+      }
+      // ---- phase 1 (tile jj): eta = X_tile beta ----
+      {
+        const double* ar = sxn + lr * P + lc;
+#pragma unroll
+        for (int kk = 0; kk < KS; ++kk) {
+          const double a = (4 * kk + lc < P) ? ar[4 * kk] : 0.0;
+          dmma(e4[kk & 3], a, bf[kk]);
+        }
+      }
+      // ---- tile jj - 1: residuals on the C fragment (row lr, chains 2 lc and 2 lc + 1) ----
+      double r[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const double et = ep[i];
+        const double ex = exp_nonpos(-fabs(et));
+        const double inv = rcp_pos(1.0 + ex);
+        const double sig = (et >= 0.0) ? inv : ex * inv;
+        r[i] = okp ? (yp - sig) : 0.0;
+        if (anyneed) {               // CTA-uniform: some chain ends a pass with this step
+          const double term = yp * et - (fmax(et, 0.0) + log1p_unit(ex, inv));
+          if (i == 0) lp0 += (nl0 && okp) ? term : 0.0;
+          else lp1 += (nl1 && okp) ? term : 0.0;
+        }
+      }
+      // C fragment -> B fragments: B[k = row lc (+4)][n = chain lr] lives in lane 4 row + lr / 2, element lr & 1
+      const int s0 = 4 * lc + (lr >> 1), s1 = 4 * (4 + lc) + (lr >> 1);
+      const double x00 = __shfl_sync(0xffffffffu, r[0], s0), x01 = __shfl_sync(0xffffffffu, r[1], s0);
+      const double x10 = __shfl_sync(0xffffffffu, r[0], s1), x11 = __shfl_sync(0xffffffffu, r[1], s1);
+      const double b0 = (lr & 1) ? x01 : x00, b1 = (lr & 1) ? x11 : x10;
+      // ---- phase 2 (tile jj - 1): grad[coord 8 ct + lr][chain] += X[n0 + k][coord] r[k][chain]; r = 0 in trip 0 ----
+      {
+        const double* at0 = sxp + lc * P + lr;
+        const double* at1 = sxp + (4 + lc) * P + lr;
+#pragma unroll
+        for (int ct = 0; ct < CT; ++ct) dmma(ga[ct], at0[8 * ct], b0);
+#pragma unroll
+        for (int ct = 0; ct < CT; ++ct) dmma(ga[ct], at1[8 * ct], b1);
+      }
+      ep[0] = (e4[0][0] + e4[1][0]) + (e4[2][0] + e4[3][0]);
+      ep[1] = (e4[0][1] + e4[1][1]) + (e4[2][1] + e4[3][1]);
+      yp = yn;
+      okp = okn;
+      sxp = sxn;
+      __syncwarp();      // every lane is done with the stage of tile jj - 1 before lane 0 refills it
+    }
+    gt += (uint32_t)mine;
+
+    // ---- combine the 8 warps' partial gradients (fixed order) through the idle rings ----
+#pragma unroll
+    for (int ct = 0; ct < CT; ++ct) {
+      myring[(ct * 32 + lane) * 2] = ga[ct][0];
+      myring[(ct * 32 + lane) * 2 + 1] = ga[ct][1];
+    }
+    {
+      double v0 = lp0, v1 = lp1;
+#pragma unroll
+      for (int off = 16; off >= 4; off >>= 1) {
+        v0 += __shfl_xor_sync(0xffffffffu, v0, off);
+        v1 += __shfl_xor_sync(0xffffffffu, v1, off);
+      }
+      if (lr == 0) { lps[w * C + 2 * lc] = v0; lps[w * C + 2 * lc + 1] = v1; }
+    }
+    __syncthreads();
+    for (int o = tid; o < C * PMAX; o += NTC) {
+      const int c = o / PMAX, k = o % PMAX;
+      double s = 0.0;
+      if (k < P) {
+        // ga[ct = k / 8] of lane (k % 8) * 4 + c / 2, element c & 1
+        const int idx = ((k >> 3) * 32 + (k & 7) * 4 + (c >> 1)) * 2 + (c & 1);
+#pragma unroll
+        for (int ww = 0; ww < NW; ++ww) s += ring[ww * WSTAGE + idx];
+      }
+      gs[c * PMAX + k] = s;
+    }
+    __syncthreads();
+    // a diverged chain may have left non-finite partials in the ring: stale reads must stay finite
+#pragma unroll
+    for (int ct = 0; ct < CT; ++ct) {
+      myring[(ct * 32 + lane) * 2] = 0.0;
+      myring[(ct * 32 + lane) * 2 + 1] = 0.0;
+    }
+    __syncwarp();
+    // the rings are rewritten by bulk copies (async proxy) in the next evaluation
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+
+  // gradient of this warp's chain (after coop_eval); returns this thread's partial of lp
+  __device__ __forceinline__ double collect(const double (&q)[E], double (&g)[E]) const {
+    const int w = threadIdx.x >> 5, t = threadIdx.x & 31;
+    double qq = 0.0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int k = coord_of<G>(e, t);
+      g[e] = (k < P) ? fma(-itau2, q[e], gs[w * PMAX + k]) : 0.0;
+      qq = fma(q[e], q[e], qq);
+    }
+    double lp = -0.5 * itau2 * qq;
+    if (t == 0) {
+#pragma unroll
+      for (int ww = 0; ww < NW; ++ww) lp += lps[ww * C + w];
+    }
+    return lp;
+  }
+};
+template <int G, int E2>
+using LogRegMma32T = LogRegMmaTP<G, E2, 32>;
+template <int G, int E2>
+using LogRegMma104T = LogRegMmaTP<G, E2, 104>;
+
+}  // namespace wn
