@@ -49,6 +49,10 @@ extern "C" {
 #define WN_TARGET_CORR_GAUSS 5   /* targetDistr.corrGauss :25-31 (2-d, rho = 0.5)             */
 #define WN_TARGET_FUNNEL_PKG 6   /* test/targets.py:23-29 (different density from funnel10)   */
 
+/* User-defined CUDA targets (the role of the reference's arbitrary Python lpFun / logp, grad callables and of
+ * walnuts_stan.py's compiled model): ids returned by wn_register_user_target() start here. */
+#define WN_TARGET_USER_BASE 1000
+
 /* transition semantics */
 #define WN_MODE_WALNUTSPY 0 /* WALNUTSpy/WALNUTS.py + adaptiveIntegrators.py */
 #define WN_MODE_PACKAGE 1   /* walnuts/walnuts.py */
@@ -96,6 +100,11 @@ int wn_abi_version(void);
 /* name -> WN_TARGET_* ("std_normal","diag_gauss","funnel","logreg","stock_watson",
  * "corr_gauss","funnel_pkg"); <0 if unknown. */
 int wn_target_id(const char* name);
+
+/* Load a user-target plug-in (built by walnuts_b200.targets.cuda_target() from csrc/wn_user_api.cuh, the user's
+ * WN_TARGET_LP_GRAD function and csrc/wn_user_plugin.cuh) and return its target id (>= WN_TARGET_USER_BASE),
+ * or <0.  The plug-in fixes the dimension d; its data array travels with wn_set_data(h, "data", ...). */
+int wn_register_user_target(const char* plugin_path);
 
 int wn_create(const wn_config* cfg, wn_handle** out);
 void wn_destroy(wn_handle* h);

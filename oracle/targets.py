@@ -169,3 +169,56 @@ def funnel_grad(q):
     grad[0] = -(q[0] / 9 - 0.25 * np.dot(q[1:], q[1:]) / np.exp(0.5 * q[0]))
     grad[1:] = -1 / np.exp(0.5 * q[0]) * q[1:]
     return grad
+
+
+# ---- the remaining reference targets (CUDA side: user targets of walnuts_b200/targets.py) --------------------------
+def smile(q, hessian=False):
+    """targetDistr.smileDistr :34-38 (= test/targets.py rosenbrock :17-21)."""
+    lp = -0.5 * q[0] ** 2 - 0.5 * (q[1] - q[0] ** 2) ** 2
+    return [lp, np.array([-q[0] + 2.0 * q[0] * q[1] - 2.0 * q[0] ** 3, q[0] ** 2 - q[1]])]
+
+
+def mod_funnel(q, hessian=False):
+    """targetDistr.modFunnel :41-51."""
+    x, y = q[0], q[1]
+    t1 = np.exp(-3.0 * x)
+    t2 = 1.0 + t1
+    t3 = 1.0 / t2
+    t4 = y ** 2
+    lp = -0.5 * (t2 * t4 + np.log(t3) + x ** 2)
+    return [lp, np.array([1.5 * t1 * (t4 - t3) - x, -y * t2])]
+
+
+def funnel1(q, hessian=False):
+    """targetDistr.funnel1 :88-92 with the closed-form normal log-pdf (the reference calls scipy)."""
+    ex = np.exp(-q[0])
+    lp = (-((q[0] / 3.0) ** 2) / 2.0 - LOG_SQRT_2PI - np.log(3.0)) + (-0.5 * ex * q[1] ** 2 - LOG_SQRT_2PI - 0.5 * q[0])
+    return [lp, np.array([-0.5 - q[0] / 9.0 + 0.5 * q[1] ** 2 * ex, -q[1] * ex])]
+
+
+def funnel10_rescaled(q, hessian=False):
+    """targetDistr.funnel10rescaled :81-86."""
+    S = np.ones(11)
+    S[0] = 3.0
+    lp, g = funnel10(S * q)
+    return [lp, S * g]
+
+
+def correlated_normal_lpdf(q):
+    """test/targets.py:9-11."""
+    rho = 0.5
+    return -0.5 * q[0] ** 2 - 0.5 / (1 - rho ** 2) * (q[1] - rho * q[0]) ** 2
+
+
+def correlated_normal_grad(q):
+    """test/targets.py:12-15 (as written there: not the derivative of the density in component 0)."""
+    rho = 0.5
+    return np.array([-q[0] + rho * q[1], (-q[1] + rho * q[0]) / (1 - rho ** 2)])
+
+
+def rosenbrock_lpdf(q):
+    return smile(q)[0]
+
+
+def rosenbrock_grad(q):
+    return smile(q)[1]

@@ -46,6 +46,28 @@ def test_python_callables_are_rejected_loudly(cuda_lib):
         wb.WALNUTS(wb.targets.stdGauss, np.zeros(3), generated=lambda q: q[:1], numIter=1, warmupIter=0, recordOrbitStats=True)
 
 
+def test_user_target_plugin_builds_and_registers(cuda_lib):
+    """cuda_target(): nvcc cross-compiles the plug-in here; the C-ABI loads it and hands out a target id; the
+    dimension baked into the plug-in is enforced (no compute calls; no GPU needed)."""
+    import walnuts_b200 as wb
+    from walnuts_b200 import _ffi
+    tg = wb.targets.smileDistr.compile()
+    assert os.path.isfile(tg.plugin)
+    dl = C.CDLL(tg.plugin)
+    for sym in ("wn_user_abi", "wn_user_dim", "wn_user_plan", "wn_user_occupancy", "wn_user_launch"):
+        assert hasattr(dl, sym)
+    assert dl.wn_user_dim() == 2 and dl.wn_user_abi() == cuda_lib.wn_abi_version()
+    tid, data = wb.targets.resolve(tg, 2)
+    assert tid >= 1000 and data == {} and _ffi.register_user_target(tg.plugin) == tid
+    with pytest.raises(ValueError):
+        wb.targets.resolve(tg, 3)
+    with pytest.raises(ValueError):
+        wb.targets.cuda_target("", 33)
+    with pytest.raises(RuntimeError, match="nvcc failed"):
+        wb.targets.cuda_target("WN_TARGET_LP_GRAD(q, g, data, n_data) { return undefined_symbol; }", 2, name="broken")
+    assert cuda_lib.wn_register_user_target(b"/nonexistent.so") < 0
+
+
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     from walnuts_b200 import _ffi, build
     monkeypatch.setattr(_ffi, "_lib", None)

@@ -12,7 +12,7 @@ DIAG_COLS = 24
 ERRORS = {-1: "WN_EINVAL", -2: "WN_ECUDA", -3: "WN_ENOMEM", -4: "WN_EUNSUPPORTED", -5: "WN_ESTATE"}
 
 # every symbol include/walnuts_cuda.h declares
-SYMBOLS = ["wn_abi_version", "wn_target_id", "wn_create", "wn_destroy", "wn_set_data", "wn_set_aux", "wn_set_adapt", "wn_set_state",
+SYMBOLS = ["wn_abi_version", "wn_target_id", "wn_register_user_target", "wn_create", "wn_destroy", "wn_set_data", "wn_set_aux", "wn_set_adapt", "wn_set_state",
            "wn_get_state", "wn_run", "wn_run_stats", "wn_run_async", "wn_sync", "wn_last_kernel_ms", "wn_last_launches",
            "wn_last_grad_evals", "wn_moments", "wn_stream", "wn_last_error", "wn_fp64_peak"]
 
@@ -55,6 +55,7 @@ def load():
     lib.wn_destroy.argtypes = [vp]
     lib.wn_destroy.restype = None
     lib.wn_set_data.argtypes = [vp, C.c_char_p, dp, C.c_int64, C.c_int]
+    lib.wn_register_user_target.argtypes = [C.c_char_p]
     lib.wn_set_aux.argtypes = [vp, C.c_char_p, C.c_double]
     lib.wn_set_adapt.argtypes = [vp, C.c_int64, C.c_int, C.c_double, C.c_int, C.c_double, C.c_double]
     lib.wn_set_state.argtypes = [vp, dp, C.c_int]
@@ -76,3 +77,16 @@ def load():
         getattr(lib, name)
     _lib = lib
     return lib
+
+
+_user_ids = {}
+
+
+def register_user_target(path):
+    """Load a user-target plug-in once per process; returns its integer target id."""
+    if path not in _user_ids:
+        rc = load().wn_register_user_target(os.fsencode(path))
+        if rc < 0:
+            raise WalnutsError(f"wn_register_user_target({path}): {ERRORS.get(rc, rc)}")
+        _user_ids[path] = rc
+    return _user_ids[path]

@@ -1,5 +1,7 @@
 // C-ABI of the B200-native WALNUTS/NUTS sampler (include/walnuts_cuda.h).
 // Host side: handle management, kernel dispatch by (target, dimension), launch + timing.
+#include <dlfcn.h>
+
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -58,7 +60,36 @@ static int fail(wn_handle* h, int code, const std::string& msg) {
   } while (0)
 
 // kernel dispatch: wn_dispatch.cuh; one translation unit per kernel family (plans_*.cu) so they compile in parallel
+
+// User targets: plug-in libraries built by walnuts_b200.targets.cuda_target() from
+// csrc/wn_user_api.cuh + the user's source + csrc/wn_user_plugin.cuh.  Target ids >= WN_TARGET_USER_BASE.
+struct UserTarget {
+  void* dl;
+  int d;
+  int (*plan)(int, int*, int*, int*, size_t*, int*);
+  int (*occupancy)(int, int);
+  int (*launch)(int, int, const void*, unsigned, void*);
+};
+static std::vector<UserTarget>& user_targets() {
+  static std::vector<UserTarget> v;
+  return v;
+}
+static const UserTarget* user_target(int id) {
+  const int i = id - WN_TARGET_USER_BASE;
+  return (i >= 0 && i < (int)user_targets().size()) ? &user_targets()[i] : nullptr;
+}
+static int user_family(const wn_config& c) { return c.mode == WN_MODE_PACKAGE ? FAM_PKG : FAM_EXT; }
+
 static bool pick_plan(const wn_config& c, bool adapt, LaunchPlan& p) {
+  if (c.target >= WN_TARGET_USER_BASE) {
+    const UserTarget* u = user_target(c.target);
+    if (!u || u->d != c.d) return false;
+    int pkg = 0;
+    p.fn = nullptr;   // launched inside the plug-in
+    u->plan(user_family(c), &p.G, &p.E2, &p.NT, &p.smem, &pkg);
+    p.package = pkg != 0;
+    return true;
+  }
   if (c.mode == WN_MODE_PACKAGE) return wn_pick_plan_pkg(c, p);
   if (c.integrator > WN_INT_YOSHIDA) return wn_pick_plan_ext(c, p);
   return adapt ? wn_pick_plan_adapt(c, p) : wn_pick_plan_wpy(c, p);
@@ -113,6 +144,26 @@ __global__ void fp64_fma_kernel(double* out, int iters, double a, double b) {
 extern "C" {
 
 int wn_abi_version(void) { return WN_ABI_VERSION; }
+
+int wn_register_user_target(const char* path) {
+  if (!path) return WN_EINVAL;
+  void* dl = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+  if (!dl) return WN_EINVAL;
+  UserTarget u;
+  u.dl = dl;
+  auto abi = (int (*)(void))dlsym(dl, "wn_user_abi");
+  auto dim = (int (*)(void))dlsym(dl, "wn_user_dim");
+  u.plan = (int (*)(int, int*, int*, int*, size_t*, int*))dlsym(dl, "wn_user_plan");
+  u.occupancy = (int (*)(int, int))dlsym(dl, "wn_user_occupancy");
+  u.launch = (int (*)(int, int, const void*, unsigned, void*))dlsym(dl, "wn_user_launch");
+  if (!abi || !dim || !u.plan || !u.occupancy || !u.launch || abi() != WN_ABI_VERSION) {
+    dlclose(dl);
+    return WN_EUNSUPPORTED;
+  }
+  u.d = dim();
+  user_targets().push_back(u);
+  return WN_TARGET_USER_BASE + (int)user_targets().size() - 1;
+}
 
 int wn_target_id(const char* name) {
   if (!name) return WN_EINVAL;
@@ -229,6 +280,11 @@ int wn_set_data(wn_handle* h, const char* key, const double* ptr, int64_t n, int
     h->n_p1 = n;
     return upload(h, &h->d_p1, ptr, n, on_device);
   }
+  if (!strcmp(key, "data")) {   // user targets: the array handed to the user's lp_grad
+    if (c.target < WN_TARGET_USER_BASE) return fail(h, WN_EINVAL, "data key \"data\" belongs to user targets");
+    h->n_p0 = n;
+    return upload(h, &h->d_p0, ptr, n, on_device);
+  }
   if (!strcmp(key, "tau")) {
     if (on_device) return fail(h, WN_EINVAL, "tau must be a host scalar");
     h->tau = ptr[0];
@@ -334,9 +390,15 @@ static int run_async_impl(wn_handle* h, int64_t n_iter, double* d_draws, double*
   const bool adapting = h->d_adapt_state != nullptr && h->iter_done < (uint32_t)h->warmup_iter;
   if (!pick_plan(c, adapting, p)) return fail(h, WN_EUNSUPPORTED, "no CUDA kernel for this target/dimension");
   CUDA_TRY(h, cudaSetDevice(c.device));
-  CUDA_TRY(h, cudaFuncSetAttribute(p.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+  const UserTarget* ut = user_target(c.target);
   int occ = 0;
-  CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, p.fn, p.NT, p.smem));
+  if (ut) {
+    occ = ut->occupancy(user_family(c), c.device);
+    if (occ < 0) return fail(h, WN_ECUDA, "user target plug-in: occupancy query failed");
+  } else {
+    CUDA_TRY(h, cudaFuncSetAttribute(p.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, p.fn, p.NT, p.smem));
+  }
   if (occ < 1) return fail(h, WN_ECUDA, "kernel does not fit on an SM");
   const int gpb = p.NT / p.G;
   long long blocks = (long long)h->num_sms * occ;
@@ -390,7 +452,12 @@ static int run_async_impl(wn_handle* h, int64_t n_iter, double* d_draws, double*
     P.nevalF = (unsigned long long*)d_nevalF; P.nevalB = (unsigned long long*)d_nevalB;
     P.totals = h->d_totals; P.scratch = h->d_scratch; P.nslot = nslot; P.queue = h->d_queue; P.tp = tp;
     void* args[] = {&P};
-    CUDA_TRY(h, cudaLaunchKernel(p.fn, dim3((unsigned)blocks), dim3(p.NT), args, p.smem, h->stream));
+    if (ut) {
+      const int rc = ut->launch(user_family(c), c.device, &P, (unsigned)blocks, h->stream);
+      if (rc) return fail(h, WN_ECUDA, "user target plug-in: kernel launch failed (" + std::to_string(rc) + ")");
+    } else {
+      CUDA_TRY(h, cudaLaunchKernel(p.fn, dim3((unsigned)blocks), dim3(p.NT), args, p.smem, h->stream));
+    }
   } else {
     PkgParams P;
     memset(&P, 0, sizeof(P));
@@ -403,7 +470,12 @@ static int run_async_impl(wn_handle* h, int64_t n_iter, double* d_draws, double*
     P.neval = (unsigned long long*)d_nevalF; P.totals = h->d_totals;
     P.scratch = h->d_scratch; P.nslot = nslot; P.queue = h->d_queue; P.tp = tp;
     void* args[] = {&P};
-    CUDA_TRY(h, cudaLaunchKernel(p.fn, dim3((unsigned)blocks), dim3(p.NT), args, p.smem, h->stream));
+    if (ut) {
+      const int rc = ut->launch(user_family(c), c.device, &P, (unsigned)blocks, h->stream);
+      if (rc) return fail(h, WN_ECUDA, "user target plug-in: kernel launch failed (" + std::to_string(rc) + ")");
+    } else {
+      CUDA_TRY(h, cudaLaunchKernel(p.fn, dim3((unsigned)blocks), dim3(p.NT), args, p.smem, h->stream));
+    }
   }
   CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
   h->iter_done += (uint32_t)n_iter;

@@ -99,10 +99,12 @@ static bool pick_plan_family(const wn_config& c, LaunchPlan& p) {
     }
     case WN_TARGET_FUNNEL:
       if constexpr (FAM == FAM_WPY) {
-        if (c.d <= 12) {   // BASELINE config 3 (funnel10): one thread per chain
+        if (c.d <= 16) {
+          // BASELINE config 3 (funnel10, d = 11): 4 threads per chain (8 chains per warp), measured +30 % over
+          // one thread per chain (WN_VARIANT=1; less divergence in the cold path, 207 instead of 255 registers)
           const char* v = getenv("WN_VARIANT");
-          if (v && atoi(v) == 1) p = plan_wpy<FunnelT, 1, 6, 128, 3>();
-          else p = plan_wpy<FunnelT, 1, 6, 128, 1>();
+          if (v && atoi(v) == 1 && c.d <= 12) p = plan_wpy<FunnelT, 1, 6, 128, 1>();
+          else p = plan_wpy<FunnelT, 4, 2, 128, 1>();
           return true;
         }
       }

@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
         if (--steps_left != 0u) continue;
         st = ST_PASS_END;
       }
-    } else if (!EXT && st == ST_RUN) {
+    } else if (st == ST_RUN) {
       if (yoshida) {
         // one leapfrog of the 4th-order triple (coefficients firstLast, middle, firstLast, :157-173); the
         // energy (Hams[i], :175) and its finiteness only count after the third
@@ -1027,9 +1027,10 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
       C.h = h;
       const double Ham0 = C.side ? C.endH1 : C.endH0;
       C.Ham0 = Ham0;
-      if constexpr (EXT) {
+      if (EXT && P.kind >= KIND_FLOW) {
         // ---- extended integrators: the whole macro step runs here (simple loops, group reductions); the
-        // driver above / below is shared.  Registers hold S = (q, vv = xi v, g).  Not a tuned path. ----
+        // driver above / below is shared.  Registers hold S = (q, vv = xi v, g).  Not a tuned path.
+        // (EXT kernels are supersets: the four hot-path integrators take the flat loop as everywhere else.) ----
         const double delta = C.delta;
         const int maxC = P.maxC;
         const double NaN = __longlong_as_double(0x7ff8000000000000ll);
@@ -1284,7 +1285,7 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
         C.nF = C.nF + nF;
         C.nB = C.nB + nB;
         C.If = If; C.Ib = Ib; C.cSim = If; C.lwt = lwt; C.Hfwd = HO;
-        if constexpr (ADAPT) C.igr = igr;
+        if constexpr (ADAPT) { C.igr = igr; trackH = false; }
         st = ST_LEAF;
         break;
       }
