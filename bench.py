@@ -313,6 +313,10 @@ def main():
                      "traffic": 0.98e9 * (evals / max(1, args.steps)) / 3.26e8,
                      "flop_per_eval": FLOP_PER_DIM_PER_EVAL * D, "achieved_at_12_flop_per_coord": ach * 12 / 8,
                      "peak_source": peak_src,
+                     # SURVEY.md 8(d) streaming model: 48 d bytes per evaluation if (q, v, g) were re-read and
+                     # re-written every micro-step; what HBM would have to deliver at the measured rate
+                     "hbm": {"streaming_model_gbs": value / max(1, world) * 48 * D / 1e9, "peak_gbs": hbm_peak,
+                             "streaming_model_over_peak": value / max(1, world) * 48 * D / 1e9 / hbm_peak},
                      "note": "register-resident chains: FP64 FMA pipe bound, not HBM (SURVEY.md 8d); "
                              f"HBM peak {hbm_peak} GB/s is not the limiter"},
         "lib": os.path.relpath(_ffi.lib_path(), ROOT),
