@@ -234,8 +234,12 @@ struct StockWatsonT {
 
   // inclusive scan over the threads of the group of NV channels; FWD: prefix, else suffix.
   // On return x = inclusive value, ex = exclusive value (sum over strictly preceding / following threads).
-  template <int NV, bool FWD>
-  __device__ __forceinline__ static void scan(double (&x)[NV], double (&ex)[NV], double* red, int& parity) {
+  // NB > 0: additionally broadcasts bc[0..NB-1] of the group's thread 0 to every thread; the values ride on the
+  // scan's own shared-memory exchange (free slots of warp 0's row) instead of costing a scan channel each.
+  template <int NV, bool FWD, int NB = 0>
+  __device__ __forceinline__ static void scan(double (&x)[NV], double (&ex)[NV], double* red, int& parity,
+                                              double* bc = nullptr) {
+    static_assert(NV + NB <= 8, "one row of the exchange buffer per warp");
     const int lane = threadIdx.x & 31;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
@@ -258,6 +262,12 @@ struct StockWatsonT {
 #pragma unroll
         for (int k = 0; k < NV; ++k) buf[w * 8 + k] = x[k];
       }
+      if constexpr (NB > 0) {
+        if ((threadIdx.x % G) == 0) {
+#pragma unroll
+          for (int j = 0; j < NB; ++j) buf[NV + j] = bc[j];
+        }
+      }
       __syncthreads();
 #pragma unroll
       for (int k = 0; k < NV; ++k) {
@@ -267,7 +277,14 @@ struct StockWatsonT {
         x[k] += off;
         ex[k] += off;
       }
+      if constexpr (NB > 0) {
+#pragma unroll
+        for (int j = 0; j < NB; ++j) bc[j] = buf[NV + j];
+      }
       parity ^= 1;
+    } else if constexpr (NB > 0) {
+#pragma unroll
+      for (int j = 0; j < NB; ++j) bc[j] = __shfl_sync(0xffffffffu, bc[j], 0);
     }
   }
 
@@ -277,7 +294,7 @@ struct StockWatsonT {
     // (temporaries are kept to 8 arrays of B doubles: the kernel is register-bound)
     // ---- phase 1: prefix sums of the innovations; index-0 entries and tS travel as "base" channels ----
     double locZ[B], locX[B];
-    double ch[5] = {0.0, 0.0, 0.0, 0.0, 0.0}, ex1[5];
+    double ch[2] = {0.0, 0.0}, ex1[2];
 #pragma unroll
     for (int i = 0; i < B; ++i) {
       const int k = k0 + i;
@@ -286,13 +303,13 @@ struct StockWatsonT {
       locZ[i] = ch[0];      // local inclusive prefix
       locX[i] = ch[1];
     }
-    if (t == 0) { ch[2] = q[0]; ch[3] = q[B]; ch[4] = q[3 * B]; }
-    scan<5, true>(ch, ex1, red, parity);
-    const double Z0 = ch[2], X0 = ch[3], tS = ch[4];
+    double b1[3] = {q[0], q[B], q[3 * B]};      // thread 0's z1, x1, tS travel with the scan's exchange
+    scan<2, true, 3>(ch, ex1, red, parity, b1);
+    const double Z0 = b1[0], X0 = b1[1], tS = b1[2];
     const double sigma = exp(-0.5 * tS), etS = exp(tS);
     double lp = 0.0;
     double ez[B], w[B], c[B], locC[B];
-    double ch2[2] = {0.0, 0.0}, ex2[2];
+    double ch2[1] = {0.0}, ex2[1];
     const double ez_prev = exp(0.5 * fma(sigma, ex1[0], Z0));   // exp(z_{k0-1}/2)
 #pragma unroll
     for (int i = 0; i < B; ++i) {
@@ -308,10 +325,10 @@ struct StockWatsonT {
       ch2[0] += c[i];
       locC[i] = ch2[0];
     }
-    if (t == 0) ch2[1] = q[2 * B];
     // ---- phase 2: tau ----
-    scan<2, true>(ch2, ex2, red, parity);
-    const double U0 = ch2[1];
+    double b2[1] = {q[2 * B]};                   // thread 0's tau1
+    scan<1, true, 1>(ch2, ex2, red, parity, b2);
+    const double U0 = b2[0];
     // residuals and their local suffix sums in one reverse sweep
     double sufR[B], sufA[B];
     double ch3[2] = {0.0, 0.0}, ex3[2];
