@@ -100,6 +100,28 @@ def test_user_target_with_data_matches_builtin(cuda_lib):
     assert np.array_equal(d1[..., EXACT], d2[..., EXACT])
 
 
+def test_user_target_d40_spilled_state(cuda_lib):
+    """d = 40: beyond what one thread keeps in registers (state in thread-local memory); same draws as the built-in."""
+    import walnuts_b200 as wb
+    d = 40
+    sigma = np.logspace(-1, 1, d)
+    src = """
+    WN_TARGET_LP_GRAD(q, g, data, n_data) {
+      double lp = 0.0;
+      for (int i = 0; i < WN_D; ++i) { g[i] = -q[i] * data[i]; lp += q[i] * g[i]; }
+      return 0.5 * lp;
+    }"""
+    tg = wb.targets.cuda_target(src, d, data=1.0 / sigma ** 2, name="my_diag40")
+    q0 = np.random.default_rng(2).standard_normal((3, d)) * sigma
+    kw = dict(integrator=wb.adaptLeapFrogR2P, H0=0.25, delta0=0.3, numIter=15, warmupIter=0, M=6, adaptH=False,
+              adaptDelta=False, seed=12)
+    s1, d1 = wb.WALNUTS(tg, q0, **kw)
+    s2, d2 = wb.WALNUTS(wb.targets.diag_gauss(sigma), q0, **kw)
+    ok, err = close(s1, s2)
+    assert ok, err
+    assert np.array_equal(d1[..., EXACT], d2[..., EXACT])
+
+
 @pytest.mark.parametrize("name", ["correlated_normal", "rosenbrock"])
 def test_user_target_package_mode(cuda_lib, name):
     """walnuts(rng, theta_init, logp, grad, ...) of the package (walnuts.py:362) on test/targets.py's remaining

@@ -8,7 +8,7 @@
 //     }
 //
 // which walnuts_b200.targets.cuda_target() compiles with nvcc for sm_100a into a plug-in library next to the
-// sampler kernels (one thread per chain; WN_D <= 32).  This header is included BEFORE the user's source.
+// sampler kernels (one thread per chain; WN_D <= 64).  This header is included BEFORE the user's source.
 #pragma once
 #include <cmath>
 #include <cstdint>
