@@ -37,6 +37,9 @@ CFG = dict(integrator="R2P", H0=0.5, delta=0.3, M=10, minC=0, maxC=10, jitter=0.
 # per-step energy (2 more FMAs); the kernel evaluates energies only where the algorithm consumes them (last
 # step of each pass), so the conservative 8 is used as numerator -- see DESIGN.md section 6.
 FLOP_PER_DIM_PER_EVAL = 8
+# What the kernel EXECUTES on interior steps of a pass: the closing and opening half kicks of neighbouring steps are
+# merged into one FMA (q+=h*v, g=-q*s, v+=h*g = 3 FP64 instructions = 6 flop); reported next to the algorithmic figure.
+EXECUTED_FLOP_PER_DIM_PER_EVAL = 6
 SEED = 20251017
 MONITOR = 16                      # coordinates monitored for ESS (spread over the sigma range)
 
@@ -312,6 +315,8 @@ def main():
                      # profiles/r01_walnutspy_diag1000_R2P.txt), scaled to the evaluations of one bench launch
                      "traffic": 0.98e9 * (evals / max(1, args.steps)) / 3.26e8,
                      "flop_per_eval": FLOP_PER_DIM_PER_EVAL * D, "achieved_at_12_flop_per_coord": ach * 12 / 8,
+                     "executed_flop_per_eval": EXECUTED_FLOP_PER_DIM_PER_EVAL * D,
+                     "executed_frac": ach * EXECUTED_FLOP_PER_DIM_PER_EVAL / FLOP_PER_DIM_PER_EVAL / peak,
                      "peak_source": peak_src,
                      # SURVEY.md 8(d) streaming model: 48 d bytes per evaluation if (q, v, g) were re-read and
                      # re-written every micro-step; what HBM would have to deliver at the measured rate

@@ -70,8 +70,9 @@ struct DiagGaussT {
   // upper bound of max(|q'|,|v'|) / max(|q|,|v|) over one leapfrog step of size hh on this target:
   // v1 = v - a s q, q' = q + hh v1, v' = v1 - a s q'  with a = hh/2, s <= smax
   __device__ __forceinline__ double step_growth(double hh) const {
+    // ... and of the merged-kick form w = v - a s q, q' = q + hh w, w' = w - hh s q' (wn_walnutspy.cuh: drift_kick)
     const double A = 0.5 * hh * smax;
-    return fmax(1.0 + hh + hh * A, 1.0 + 2.0 * A + hh * A + hh * A * A);
+    return fmax(fmax(1.0 + hh + hh * A, 1.0 + 2.0 * A + hh * A + hh * A * A), 1.0 + 2.0 * A + 2.0 * A * hh);
   }
   __device__ __forceinline__ void grad_only(const double (&q)[E], double (&g)[E]) const {
 #pragma unroll
