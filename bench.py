@@ -38,8 +38,9 @@ CFG = dict(integrator="R2P", H0=0.5, delta=0.3, M=10, minC=0, maxC=10, jitter=0.
 # step of each pass), so the conservative 8 is used as numerator -- see DESIGN.md section 6.
 FLOP_PER_DIM_PER_EVAL = 8
 # What the kernel EXECUTES on interior steps of a pass: the closing and opening half kicks of neighbouring steps are
-# merged into one FMA (q+=h*v, g=-q*s, v+=h*g = 3 FP64 instructions = 6 flop); reported next to the algorithmic figure.
-EXECUTED_FLOP_PER_DIM_PER_EVAL = 6
+# merged and, the gradient being linear, folded into ONE FMA on a per-pass coefficient (q+=h*v, v+=(-h*s)*q = 2 FP64
+# instructions = 4 flop); reported next to the algorithmic figure.
+EXECUTED_FLOP_PER_DIM_PER_EVAL = 4
 SEED = 20251017
 MONITOR = 16                      # coordinates monitored for ESS (spread over the sigma range)
 

@@ -74,6 +74,15 @@ struct DiagGaussT {
     const double A = 0.5 * hh * smax;
     return fmax(fmax(1.0 + hh + hh * A, 1.0 + 2.0 * A + hh * A + hh * A * A), 1.0 + 2.0 * A + 2.0 * A * hh);
   }
+  // The gradient is linear, g = -s q, so the full kick v += h g of the merged-kick loop is ONE FMA v += (-h s) q
+  // with the coefficient formed once per pass: 2 FP64 instructions per coordinate and interior step.
+  __device__ __forceinline__ void kick_coeffs(double hh, double (&kc)[E]) const {
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      if constexpr (UNIT) kc[e] = -hh;
+      else kc[e] = -(hh * s[e]);
+    }
+  }
   __device__ __forceinline__ void grad_only(const double (&q)[E], double (&g)[E]) const {
 #pragma unroll
     for (int e = 0; e < E; ++e) {

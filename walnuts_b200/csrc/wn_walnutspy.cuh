@@ -349,17 +349,17 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
     }
   };
   // Interior step of a skipped-energy run with MERGED kicks: the closing half kick of one step and the opening half
-  // kick of the next use the same gradient, v + a g + a g, and are issued as one FMA v + h g -- 3 instead of 4 FP64
-  // instructions per coordinate and step.  (One rounding instead of two: <= 1 ulp of v per step, the same order as
-  // the FMA contraction already documented in DESIGN.md section 5.)  v then carries the opening half kick of the
-  // next step; the run ends with micro_step(false).
-  auto drift_kick = [&]() {
-    if constexpr (Target::LAZY_ENERGY) {
+  // kick of the next use the same gradient, v + a g + a g = v + h g; with the linear gradient of the LAZY_ENERGY
+  // targets (g = -s q) that is ONE FMA v + (-h s) q on a coefficient formed once per pass.  2 instead of 4 FP64
+  // instructions per coordinate and step: q += h v; v += kc q.  (Rounding differs from the reference's two half
+  // kicks by <= 1 ulp of v per step -- the same order as the FMA contraction documented in DESIGN.md section 5;
+  // the parity suite, incl. the exact discrete diagnostics over 100 free-running transitions, is unchanged.)
+  // v carries the opening half kick of the next step; the run ends with micro_step(false), which recomputes g.
+  auto drift_kick = [&](const double (&kc)[E]) {
 #pragma unroll
-      for (int e = 0; e < E; ++e) q[e] = fma(hh, v[e], q[e]);
-      target.grad_only(q, g);
-#pragma unroll
-      for (int e = 0; e < E; ++e) v[e] = fma(hh, g[e], v[e]);
+    for (int e = 0; e < E; ++e) {
+      q[e] = fma(hh, v[e], q[e]);
+      v[e] = fma(kc[e], q[e], v[e]);
     }
   };
   constexpr int LAZY_LIMIT = (1023 + 300) << 20;
@@ -429,19 +429,21 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
         --steps_left;
         if (nh == 4 || steps_left == 0u) flush_hist();
       } else if (Target::LAZY_ENERGY && lazy && steps_left >= 3u) {
-        if constexpr (G >= 32 && !Target::BLOCK_LOCKSTEP) {
+        if constexpr (Target::LAZY_ENERGY && G >= 32 && !Target::BLOCK_LOCKSTEP) {
           // the whole warp follows one chain: stay in a tight loop for the skipped-energy steps (merged kicks),
           // then finish the pass with the one step whose energy is consumed
+          double kc[E];
+          target.kick_coeffs(hh, kc);
 #pragma unroll
           for (int e = 0; e < E; ++e) v[e] = fma(ha, g[e], v[e]);
           do {
-            drift_kick();
-            drift_kick();
+            drift_kick(kc);
+            drift_kick(kc);
             steps_left -= 2u;
             since += 2;
             if (since >= lazyK) { track_state(); since = 0; }
           } while (steps_left >= 3u);
-          if (steps_left == 2u) drift_kick();
+          if (steps_left == 2u) drift_kick(kc);
           micro_step(false);
           steps_left = 0u;
         } else {
