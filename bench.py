@@ -312,9 +312,9 @@ def main():
         "gpu_launches": args.steps * cb.last_launches(),
         "clocks": clocks,
         "roofline": {"bound": "fp64", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                     # dram__bytes_read+write of one `ncu --set full` launch (0.98 GB for 3.26e8 evaluations,
+                     # dram__bytes_read+write of one `ncu --set full` launch (0.170 + 0.768 GB for 3.206e8 evaluations,
                      # profiles/r01_walnutspy_diag1000_R2P.txt), scaled to the evaluations of one bench launch
-                     "traffic": 0.98e9 * (evals / max(1, args.steps)) / 3.26e8,
+                     "traffic": 0.938e9 * (evals / max(1, args.steps)) / 3.206e8,
                      "flop_per_eval": FLOP_PER_DIM_PER_EVAL * D, "achieved_at_12_flop_per_coord": ach * 12 / 8,
                      "executed_flop_per_eval": EXECUTED_FLOP_PER_DIM_PER_EVAL * D,
                      "executed_frac": ach * EXECUTED_FLOP_PER_DIM_PER_EVAL / FLOP_PER_DIM_PER_EVAL / peak,

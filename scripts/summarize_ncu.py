@@ -2,7 +2,12 @@
 import csv, io, subprocess, sys, collections
 
 def raw_metrics(rep):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    # a .ncu-rep, or the CSV that `ncu -i rep --page raw --csv` printed on the GPU box (the reports with imported
+    # source exceed the 64 MiB that travel back)
+    if rep.endswith(".csv"):
+        out = open(rep).read()
+    else:
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     return rows[0], rows[1], rows[2:]
 
@@ -16,10 +21,11 @@ WANT = ["Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__b
         "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
-        "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio", "smsp__sass_inst_executed_op_local_ld.sum", "smsp__sass_inst_executed_op_local_st.sum"]
+        "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio", "smsp__sass_inst_executed_op_local_ld.sum", "smsp__sass_inst_executed_op_local_st.sum",
+        "lts__t_sector_hit_rate.pct", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"]
 
 def main():
-    rep, launches, out = sys.argv[1], sys.argv[2], sys.argv[3]
+    rep, launches, out = sys.argv[1], sys.argv[2], sys.argv[3]      # launches: a csv, or "-" for none
     hdr, units, rows = raw_metrics(rep)
     with open(out, "w") as f:
         f.write(f"# ncu --set full --clock-control none --import-source on  ({rep})\n")
@@ -29,6 +35,10 @@ def main():
                     if h == w:
                         f.write(f"{h} [{units[i]}] = {r[i]}\n")
             f.write("\n")
+        if launches == "-":
+            f.flush()
+            print(open(out).read())
+            return
         # launch list
         f.write(f"# launch list: ncu --metrics gpu__time_duration.sum --clock-control none  ({launches})\n")
         txt = open(launches).read()
