@@ -32,15 +32,14 @@ sys.path.insert(0, ROOT)
 D = 1000
 CHAINS_PER_GPU = 65536
 CFG = dict(integrator="R2P", H0=0.5, delta=0.3, M=10, minC=0, maxC=10, jitter=0.2)
-# Algorithmic FP64 work per gradient evaluation and coordinate: v+=a*g, q+=h*v, g=-q*s, v+=a*g = 4 FP64
-# instructions = 8 flop (7 strictly; an FMA counts 2).  SURVEY.md section 8(d) quotes 12 flop including the
-# per-step energy (2 more FMAs); the kernel evaluates energies only where the algorithm consumes them (last
-# step of each pass), so the conservative 8 is used as numerator -- see DESIGN.md section 6.
-FLOP_PER_DIM_PER_EVAL = 8
-# What the kernel EXECUTES on interior steps of a pass: the closing and opening half kicks of neighbouring steps are
-# merged and, the gradient being linear, folded into ONE FMA on a per-pass coefficient (q+=h*v, v+=(-h*s)*q = 2 FP64
-# instructions = 4 flop); reported next to the algorithmic figure.
-EXECUTED_FLOP_PER_DIM_PER_EVAL = 4
+# FP64 work per gradient evaluation (= one leapfrog micro-step) and coordinate.  The reference's formulation is
+# v+=a*g, q+=h*v, g=-q*s, v+=a*g = 4 FP64 instructions = 8 flop, 12 with the per-step energy SURVEY.md 8(d) quotes.
+# The algorithm itself needs less: the closing and the opening half kick of neighbouring steps use the same gradient
+# and merge, and the gradient of this target is linear, so an interior step is q+=h*v, v+=(-h*s)*q = 2 FMAs = 4 flop
+# (energies are only consumed at the end of a pass).  The kernel executes exactly that, so 4 flop per coordinate is
+# both the algorithmic minimum and the executed work; it is the roofline numerator.  The figures at the reference's
+# 8 / 12 flop per coordinate are reported next to it.
+FLOP_PER_DIM_PER_EVAL = 4
 SEED = 20251017
 MONITOR = 16                      # coordinates monitored for ESS (spread over the sigma range)
 
@@ -315,9 +314,9 @@ def main():
                      # dram__bytes_read+write of one `ncu --set full` launch (0.170 + 0.768 GB for 3.206e8 evaluations,
                      # profiles/r01_walnutspy_diag1000_R2P.txt), scaled to the evaluations of one bench launch
                      "traffic": 0.938e9 * (evals / max(1, args.steps)) / 3.206e8,
-                     "flop_per_eval": FLOP_PER_DIM_PER_EVAL * D, "achieved_at_12_flop_per_coord": ach * 12 / 8,
-                     "executed_flop_per_eval": EXECUTED_FLOP_PER_DIM_PER_EVAL * D,
-                     "executed_frac": ach * EXECUTED_FLOP_PER_DIM_PER_EVAL / FLOP_PER_DIM_PER_EVAL / peak,
+                     "flop_per_eval": FLOP_PER_DIM_PER_EVAL * D,
+                     "achieved_at_8_flop_per_coord": ach * 8 / FLOP_PER_DIM_PER_EVAL,
+                     "achieved_at_12_flop_per_coord": ach * 12 / FLOP_PER_DIM_PER_EVAL,
                      "peak_source": peak_src,
                      # SURVEY.md 8(d) streaming model: 48 d bytes per evaluation if (q, v, g) were re-read and
                      # re-written every micro-step; what HBM would have to deliver at the measured rate
