@@ -160,7 +160,13 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
     const double lo = C.jlo;
     return __dadd_rn(lo, __dmul_rn(__dadd_rn(C.jhi, -lo), u));
   };
+  // magnitude summary (track_state) of the checkpointed state: every attempt of a step-size search restarts from
+  // the same checkpoint, so its bound check is done once per checkpoint, not once per pass
+  int ckS = 0;
+  unsigned ckU = 0;
+  bool ckTracked = false;
   auto save_ck = [&]() {
+    ckTracked = false;
 #pragma unroll
     for (int e = 0; e < E; ++e) {
       ck[(0 * E + e) * NT + tid] = q[e];
@@ -275,14 +281,18 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
     if constexpr (Target::LAZY_ENERGY) {
       lazy = rlazyok && !rexact && (cc >= 2) && !trackH && !yoshida;
       if (lazy) {
-        track_state();   // the pass starts from a bounded state
+        // the pass starts from a bounded state (registers = checkpoint up to the sign of v, which the two
+        // accumulators treat symmetrically)
+        if (ckTracked) { smax = ckS; umax = ckU; }
+        else { track_state(); ckS = smax; ckU = umax; ckTracked = true; }
         since = 0;
         // One leapfrog step amplifies max(|q|,|v|) by at most Gamma (target-specific bound); checked
         // states are below 2^300, so up to floor(180 / log2 Gamma) steps may pass between checks while
         // every skipped energy stays finite (< 2^480 magnitudes).
         // (two steps of the budget are reserved for the half kick that the merged-kick loop carries in v)
-        const double lg = log2(target.step_growth(hh));
-        lazyK = (lg * 66.0 <= 180.0) ? 64 : ((int)(180.0 / lg) - 2);
+        // log2 Gamma is bounded from above by the exponent field (Gamma >= 1): integer arithmetic only
+        const int lg = ((__double2hiint(target.step_growth(hh)) >> 20) & 0x7ff) - 1022;
+        lazyK = (lg * 66 <= 180) ? 64 : ((int)__fdividef(180.0f, (float)lg) - 2);
         lazyK &= ~1;
         if (lazyK < 2) lazy = false;
       }
