@@ -133,7 +133,7 @@ def cpu_baseline(iters=1, cores=None):
     return {"value": evals / busy, "unit": "grad_evals/s", "cores": cores, "kind": "port",
             "sample": f"{cores} chains x {iters} transition(s) of the bench workload, one chain per process "
                       f"(numpy restatement of WALNUTSpy; {evals:.0f} evals in {busy:.1f}s, wall {wall:.1f}s)",
-            "per_core": evals / busy / cores}
+            "per_core": evals / busy / cores, "seconds": busy}
 
 
 def cpu_baseline_c(iters=1, cores=None, chains_per_core=4):
@@ -177,17 +177,19 @@ def main():
         if rank != 0:
             return
         cb = None
-        vals = []
+        vals, secs = [], []
         for _ in range(max(1, min(args.steps, 3))):
             cb = cpu_baseline(args.cpu_iters)
             vals.append(cb["value"])
+            secs.append(cb["seconds"])
         cb["value"] = float(np.mean(vals))
         try:
             extra_c = cpu_baseline_c(args.cpu_iters)
         except Exception as e:
             extra_c = {"unavailable": str(e)[:200]}
         line = {"impl": "reference", "cpu_baseline_c": extra_c, "metric": "grad_evals_per_sec", "value": cb["value"], "unit": "grad_evals/s",
-                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": None,
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": 1e3 * float(np.mean(secs)),     # one step = the bounded sample described in cpu_baseline
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "config": config, "cpu_baseline": cb,
                 "e2e": {"value": cb["value"], "unit": "grad_evals/s", "h2d_bytes_per_step": 0,

@@ -108,3 +108,22 @@ def test_ess_estimator():
     tot["n"] = a["n"]
     whole = dg.ess_from_stats(dg.chain_stats(y, 40))
     assert np.isclose(dg.ess_from_stats(tot)[0], whole[0], rtol=1e-12)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to ours): one JSON line with the contract keys,
+    produced by the oracle port on the host cores -- no GPU, no CUDA library involved."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "0"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "grad_evals_per_sec" and line["unit"] == "grad_evals/s"
+    assert line["higher_is_better"] is True and line["value"] > 0 and line["ms_per_step"] > 0
+    assert line["config"]["workload"].startswith("diag_gauss_d1000")
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "sample" in cb
+    assert line["e2e"] == {"value": line["value"], "unit": "grad_evals/s", "h2d_bytes_per_step": 0,
+                           "d2h_bytes_per_step": 0}
