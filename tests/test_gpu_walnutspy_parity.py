@@ -242,7 +242,9 @@ def test_stock_watson_small_T(cuda_lib):
           float_rtol=1e-6)
 
 
-@pytest.mark.parametrize("integrator,N,P", [("fixed", 500, 7), ("R2P", 500, 7), ("D", 1000, 100), ("R2P", 1333, 100)])
+@pytest.mark.parametrize("integrator,N,P", [("fixed", 500, 7), ("R2P", 500, 7), ("D", 1000, 100), ("R2P", 1333, 100),
+                                            ("D", 501, 7),      # last row tile of 5 x 7 doubles: not a bulk-copy size
+                                            ("R2P", 3, 5)])     # fewer rows than one tile, fewer tiles than warps
 def test_logreg(cuda_lib, integrator, N, P):
     """BASELINE config 4 target (P = 100 features) on small synthetic row counts, incl. a ragged N."""
     from oracle import targets as ot
