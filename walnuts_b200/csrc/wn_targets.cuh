@@ -890,8 +890,8 @@ struct LogRegMmaTP {
         : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
   }
 
-  // `gt`: number of tiles this warp has consumed so far (kept by the caller across evaluations): tile g lives in
-  // stage g % S of the warp's ring and completes phase (g / S) & 1 of that stage's mbarrier.
+  // `gt`: number of tiles this warp has consumed so far, modulo 2S (kept by the caller across evaluations): tile g
+  // lives in stage g % S of the warp's ring and completes phase (g / S) & 1 of that stage's mbarrier.
   __device__ __forceinline__ void coop_eval(uint32_t& gt) const {
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
     const int lr = lane >> 2, lc = lane & 3;       // fragment coordinates
@@ -1001,7 +1001,9 @@ struct LogRegMmaTP {
       sxp = sxn;
       __syncwarp();      // every lane is done with the stage of tile jj - 1 before lane 0 refills it
     }
-    gt += (uint32_t)mine;
+    // stage (g % S) and mbarrier phase ((g / S) & 1) only depend on g mod 2S: keep the counter bounded so that a
+    // launch of any length never wraps it
+    gt = (gt + (uint32_t)mine) % (uint32_t)(2 * S);
 
     // ---- combine the 8 warps' partial gradients (fixed order) through the idle rings ----
 #pragma unroll
