@@ -103,7 +103,8 @@ int wn_target_id(const char* name);
 
 /* Load a user-target plug-in (built by walnuts_b200.targets.cuda_target() from csrc/wn_user_api.cuh, the user's
  * WN_TARGET_LP_GRAD function and csrc/wn_user_plugin.cuh) and return its target id (>= WN_TARGET_USER_BASE),
- * or <0.  The plug-in fixes the dimension d; its data array travels with wn_set_data(h, "data", ...). */
+ * or <0.  The plug-in fixes the dimension d; its data array travels with wn_set_data(h, "data", ...).
+ * The registry is process-wide and append-only (plug-ins stay loaded); call it from one thread at a time. */
 int wn_register_user_target(const char* plugin_path);
 
 int wn_create(const wn_config* cfg, wn_handle** out);

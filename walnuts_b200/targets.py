@@ -95,16 +95,20 @@ def cuda_target(source, d, data=None, name="user", verbose=False):
     os.makedirs(out_dir, exist_ok=True)
     so = os.path.join(out_dir, f"{name}_{h.hexdigest()[:16]}.so")
     if not os.path.isfile(so):
-        src = so[:-3] + ".cu"
+        # per-process scratch names + atomic rename: several ranks may build the same plug-in at once
+        src = f"{so[:-3]}.{os.getpid()}.cu"
+        tmp = f"{so}.{os.getpid()}.tmp"
         with open(src, "w") as fh:
             fh.write(tu)
-        cmd = [os.environ.get("NVCC", "nvcc")] + _build.NVCC_FLAGS + ["-shared", "-I", csrc, "-o", so + ".tmp", src]
+        cmd = [os.environ.get("NVCC", "nvcc")] + _build.NVCC_FLAGS + ["-shared", "-I", csrc, "-o", tmp, src]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if verbose:
             print(r.stderr)
         if r.returncode != 0:
+            os.remove(src)
             raise RuntimeError("cuda_target: nvcc failed:\n" + r.stdout + r.stderr)
-        os.replace(so + ".tmp", so)
+        os.replace(src, so[:-3] + ".cu")
+        os.replace(tmp, so)
     dd = {} if data is None else {"data": np.ascontiguousarray(data, dtype=np.float64).ravel()}
     return Target(f"user:{name}", data=dd, d=d, ref="user CUDA source", plugin=so)
 
