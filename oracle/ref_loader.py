@@ -102,14 +102,15 @@ def philox_numpy_random(seed, chain, M, first_iteration=1):
 
 def run_walnutspy(lpFun, q0, integrator_name, H0, delta0, numIter, M, minC=0, maxC=10,
                   seed=0, chain=0, stepSizeRandScale=0.2, use_philox=True, np_seed=None,
-                  generated=None):
-    """Run the real WALNUTS.WALNUTS with adaptation off (fixed H, delta)."""
+                  generated=None, warmupIter=0):
+    """Run the real WALNUTS.WALNUTS; adaptation off (fixed H, delta) unless warmupIter > 0, which switches on the
+    reference's default warm-up adaptation (adaptH, adaptDelta with their default targets, WALNUTS.py:111-129)."""
     wn, ai, _ = load_walnutspy()
     integrator = getattr(ai, integrator_name)
     aux = ai.integratorAuxPar(minC=minC, maxC=maxC)
     kw = dict(q0=np.array(q0, dtype=np.float64), integrator=integrator, H0=H0,
-              stepSizeRandScale=stepSizeRandScale, delta0=delta0, numIter=numIter, warmupIter=0,
-              M=M, igrAux=aux, adaptH=False, adaptDelta=False)
+              stepSizeRandScale=stepSizeRandScale, delta0=delta0, numIter=numIter, warmupIter=warmupIter,
+              M=M, igrAux=aux, adaptH=warmupIter > 0, adaptDelta=warmupIter > 0)
     if generated is not None:
         kw["generated"] = generated
     with np.errstate(all="ignore"), contextlib.redirect_stdout(open(os.devnull, "w")):

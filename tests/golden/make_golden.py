@@ -44,6 +44,15 @@ def walnutspy_cases():
                           integrator=integ, H0=1.1, delta=dlt, M=7, n_iter=60, minC=0, maxC=10, seed=21, chain=2))
         cases.append(dict(name=f"wpy_funnel10_{integ}", target="funnel", q0=fq.copy(), integrator=integ, H0=0.4,
                           delta=dlt, M=8, n_iter=40, minC=0, maxC=10, seed=22, chain=4))
+    # warm-up adaptation with the reference's default arguments (P-squared quantile for H, quantile of the energy
+    # error for delta, WALNUTS.py:136-147,313,701-712): pins the oracle's adaptation incl. every integrator's igrConst
+    rng3 = np.random.default_rng(2027)
+    # (adaptImplicitMidpointD is left out: the implicit midpoint rule conserves a quadratic energy exactly, igrConst
+    # becomes infinite and the reference itself ends in sys.exit("numerical problems") under its default adaptation)
+    for integ in ("fixed", "D", "R2P", "Yoshida", "Flow", "Rescaled"):
+        cases.append(dict(name=f"wpy_adapt_std5_{integ}", target="std_normal", q0=0.5 * rng3.standard_normal(5),
+                          integrator=integ, H0=0.2, delta=0.05, M=7, n_iter=90, warmup=60, minC=0, maxC=10, seed=31,
+                          chain=1))
     cases.append(dict(name="wpy_std100_R2P", target="std_normal", q0=rng.standard_normal(100), integrator="R2P",
                       H0=0.9 * 100 ** -0.25, delta=0.3, M=8, n_iter=40, minC=0, maxC=10, seed=14, chain=7))
     return cases
@@ -74,7 +83,8 @@ def main():
             continue
         t0 = time.time()
         s, d = ref_loader.run_walnutspy(lp[c["target"]], c["q0"], NAMES[c["integrator"]], c["H0"], c["delta"],
-                                        c["n_iter"], c["M"], c["minC"], c["maxC"], seed=c["seed"], chain=c["chain"])
+                                        c["n_iter"], c["M"], c["minC"], c["maxC"], seed=c["seed"], chain=c["chain"],
+                                        warmupIter=c.get("warmup", 0))
         meta = {k: v for k, v in c.items() if k != "q0"}
         np.savez_compressed(os.path.join(OUT, c["name"] + ".npz"), meta=json.dumps(meta), q0=c["q0"], samples=s,
                             diagnostics=d)

@@ -175,7 +175,8 @@ import os
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 
-@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "wpy_*.npz"))), ids=os.path.basename)
+@pytest.mark.parametrize("path", sorted(p for p in glob.glob(os.path.join(GOLD, "wpy_*.npz"))
+                                        if "wpy_adapt_" not in os.path.basename(p)), ids=os.path.basename)
 def test_walnutspy_golden_from_real_reference(cuda_lib, path):
     """CUDA vs the REAL reference's stored outputs (tests/golden/make_golden.py), through the drop-in
     WALNUTS(...) surface.  Funnel cases are compared per transition on identical inputs (chaotic
