@@ -102,7 +102,7 @@ def philox_numpy_random(seed, chain, M, first_iteration=1):
 
 def run_walnutspy(lpFun, q0, integrator_name, H0, delta0, numIter, M, minC=0, maxC=10,
                   seed=0, chain=0, stepSizeRandScale=0.2, use_philox=True, np_seed=None,
-                  generated=None, warmupIter=0):
+                  generated=None, warmupIter=0, recordOrbitStats=False):
     """Run the real WALNUTS.WALNUTS; adaptation off (fixed H, delta) unless warmupIter > 0, which switches on the
     reference's default warm-up adaptation (adaptH, adaptDelta with their default targets, WALNUTS.py:111-129)."""
     wn, ai, _ = load_walnutspy()
@@ -113,6 +113,8 @@ def run_walnutspy(lpFun, q0, integrator_name, H0, delta0, numIter, M, minC=0, ma
               M=M, igrAux=aux, adaptH=warmupIter > 0, adaptDelta=warmupIter > 0)
     if generated is not None:
         kw["generated"] = generated
+    if recordOrbitStats:
+        kw["recordOrbitStats"] = True      # returns (samples, diagnostics, orbitMin, orbitMax), WALNUTS.py:724-725
     with np.errstate(all="ignore"), contextlib.redirect_stdout(open(os.devnull, "w")):
         if use_philox:
             with philox_numpy_random(seed, chain, M):

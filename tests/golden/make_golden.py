@@ -89,6 +89,16 @@ def main():
         np.savez_compressed(os.path.join(OUT, c["name"] + ".npz"), meta=json.dumps(meta), q0=c["q0"], samples=s,
                             diagnostics=d)
         print(f"{c['name']}: {time.time() - t0:.1f}s stop codes {np.unique(d[:, 19])}")
+    # recordOrbitStats=True (WALNUTS.py:182-184,274-276,...): per-iteration min / max of the states visited by the orbit
+    if want("orbit_corr_R2P"):
+        q0 = np.array([0.8, -0.3])
+        s, d, omin, omax = ref_loader.run_walnutspy(td.corrGauss, q0, "adaptLeapFrogR2P", 0.9, 0.1, 50, 7, 0, 10, seed=41,
+                                                    chain=2, recordOrbitStats=True)
+        meta = dict(name="orbit_corr_R2P", target="corr_gauss", integrator="R2P", H0=0.9, delta=0.1, M=7, n_iter=50,
+                    minC=0, maxC=10, seed=41, chain=2)
+        np.savez_compressed(os.path.join(OUT, "orbit_corr_R2P.npz"), meta=json.dumps(meta), q0=q0, samples=s,
+                            diagnostics=d, orbit_min=omin, orbit_max=omax)
+        print("orbit_corr_R2P: done")
     plp = {"std_normal": (tt.standard_normal_lpdf, tt.standard_normal_grad),
            "funnel_pkg": (tt.funnel_lpdf, tt.funnel_grad)}
     for c in package_cases():
