@@ -1,23 +1,30 @@
 #!/usr/bin/env python
-"""Headline benchmark: gradient evals/sec (and min-ESS/sec) of the many-chain WALNUTS hot path.
+"""Benchmark of the many-chain WALNUTS hot path: gradient evals/sec and min-ESS/sec.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-Workload (BASELINE.json configs[1]): 1000-d ill-conditioned diagonal Gaussian,
-sigma = logspace(-2, 2, 1000), 65 536 chains PER GPU (weak scaling), WALNUTSpy driver with
+Headline workload (BASELINE.json configs[1], the config the metric is quoted on): 1000-d ill-conditioned diagonal
+Gaussian, sigma = logspace(-2, 2, 1000), 65 536 chains PER GPU (weak scaling), WALNUTSpy driver with
 adaptLeapFrogR2P, H0 = 0.5, delta = 0.3, M = 10, minC = 0, maxC = 10.
-One "step" = `--iters` transitions of every chain (one persistent-kernel launch).
+One "step" = one transition of every chain (one persistent-kernel launch).
 
-Prints ONE JSON line (rank 0).  `value` = gradient evaluations per second with the chain states
-resident in HBM, timed with CUDA events on the handle's stream (max over ranks); `e2e` = the same
-through the public host-buffer API (H2D of the positions from pinned memory, D2H of draws,
-diagnostics and positions inside the timed region).  `--impl reference` times the CPU restatement of
-the reference Python implementation (oracle/walnutspy_oracle.py; the reference itself is Python and
-cannot travel to the GPU box) on all host cores.
+ONE JSON line (rank 0):
+  value            gradient evaluations per second, chain states resident in HBM, timed with CUDA events on the
+                   handle's stream (max over ranks)
+  e2e              the same through host buffers (wn_run_host_async on pinned memory: positions H2D, draws /
+                   diagnostics / counters / positions D2H inside the timed region; two handles per GPU so that the
+                   copies of one overlap the kernel of the other)
+  min_ess_per_sec  cross-chain bulk ESS (rank-normalised, split chains; the arviz / Stan estimator) of the slowest
+                   monitored coordinate per second of device time, from a dedicated leg with >= 1024 draws per chain
+  configs          the OTHER BASELINE configs under the same clock: C1 package-mode 100-d normal, C2 with plain NUTS,
+                   C3 funnel, C4 logistic regression, C5 Stock-Watson (131 072 chains per GPU = 1 048 576 on 8 GPUs)
+                   and 1 048 576 C2 chains on one GPU -- each with value, e2e, roofline, cpu_baseline, clocks
+  strong_scaling   the headline workload with 65 536 chains in TOTAL split over the N GPUs (N > 1)
+`--impl reference` times the CPU restatement of the reference's Python implementation (oracle/walnutspy_oracle.py;
+the reference itself is Python and cannot travel to the GPU box) on all host cores.
 """
 import argparse
 import json
-import math
 import os
 import subprocess
 import sys
@@ -29,19 +36,39 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+SEED = 20251017
 D = 1000
 CHAINS_PER_GPU = 65536
-CFG = dict(integrator="R2P", H0=0.5, delta=0.3, M=10, minC=0, maxC=10, jitter=0.2)
-# FP64 work per gradient evaluation (= one leapfrog micro-step) and coordinate.  The reference's formulation is
-# v+=a*g, q+=h*v, g=-q*s, v+=a*g = 4 FP64 instructions = 8 flop, 12 with the per-step energy SURVEY.md 8(d) quotes.
-# The algorithm itself needs less: the closing and the opening half kick of neighbouring steps use the same gradient
-# and merge, and the gradient of this target is linear, so an interior step is q+=h*v, v+=(-h*s)*q = 2 FMAs = 4 flop
-# (energies are only consumed at the end of a pass).  The kernel executes exactly that, so 4 flop per coordinate is
-# both the algorithmic minimum and the executed work; it is the roofline numerator.  The figures at the reference's
-# 8 / 12 flop per coordinate are reported next to it.
-FLOP_PER_DIM_PER_EVAL = 4
-SEED = 20251017
 MONITOR = 16                      # coordinates monitored for ESS (spread over the sigma range)
+
+# Workloads.  flop_per_eval = ALGORITHMIC FP64 work per gradient evaluation (= one leapfrog micro-step incl. the energy)
+# of SURVEY.md section 8(d); C2/R2P additionally reports the 4 flop per coordinate its kernel executes.
+WORKLOADS = {
+    "c2": dict(target="diag_gauss", d=D, mode="walnutspy", integrator="R2P", H0=0.5, delta=0.3, M=10, minC=0, maxC=10,
+               chains=CHAINS_PER_GPU, iters=1, monitor=MONITOR, flop_per_eval=12.0 * D,
+               workload="diag_gauss_d1000_sigma_logspace(-2,2)_R2P"),
+    "c1": dict(target="std_normal", d=100, mode="package", integrator="fixed", H0=2.0, delta=0.1, M=10, minC=0, maxC=10,
+               chains=65536, iters=4, monitor=8, flop_per_eval=12.0 * 100, steps_cap=5, warmup_cap=3,
+               workload="package_walnuts_std_normal_d100_macro2.0_depth10_maxerr0.1 (test/test.py:10-18)"),
+    "c2_nuts": dict(target="diag_gauss", d=D, mode="walnutspy", integrator="fixed", H0=0.008, delta=0.3, M=10, minC=0,
+                    maxC=10, chains=CHAINS_PER_GPU, iters=1, monitor=MONITOR, flop_per_eval=12.0 * D, steps_cap=5,
+                    warmup_cap=3, workload="diag_gauss_d1000_fixedLeapFrog_H0.008 (plain NUTS)"),
+    "c3": dict(target="funnel", d=11, mode="walnutspy", integrator="R2P", H0=0.3, delta=0.3, M=12, minC=0, maxC=10,
+               chains=262144, iters=10, monitor=11, flop_per_eval=200.0, steps_cap=5, warmup_cap=3,
+               workload="funnel10_R2P_M12 (mainFunnel.py:24-32)"),
+    "c4": dict(target="logreg", d=100, mode="walnutspy", integrator="R2P", H0=0.05, delta=0.3, M=6, minC=0, maxC=10,
+               chains=16384, iters=1, monitor=8, flop_per_eval=4.5e7, steps_cap=2, warmup_cap=1,
+               workload="logreg_N100000_P100_R2P"),
+    "c5": dict(target="stock_watson", d=756, mode="walnutspy", integrator="R2P", H0=0.1, delta=0.3, M=14, minC=3,
+               maxC=10, chains=131072, iters=1, monitor=8, flop_per_eval=4.0e4, steps_cap=3, warmup_cap=2,
+               workload="stock_watson_T252_R2P_M14_minC3 (mainSW.py:41-49); 131072 chains per GPU"),
+    "c2_1m": dict(target="diag_gauss", d=D, mode="walnutspy", integrator="R2P", H0=0.5, delta=0.3, M=10, minC=0,
+                  maxC=10, chains=1048576, iters=1, monitor=MONITOR, flop_per_eval=12.0 * D, steps_cap=1, warmup_cap=0,
+                  single_gpu_only=True, e2e=False,
+                  workload="diag_gauss_d1000_R2P, 1 048 576 concurrent chains on ONE GPU (kernel warm from the headline leg)"),
+}
+CONFIG_ORDER = ["c1", "c2_nuts", "c3", "c4", "c5", "c2_1m"]
+ESS_CHAINS, ESS_DRAWS = 1184, 1024      # 2 chains per resident slot of the d = 1000 kernel (148 SMs x 4 blocks)
 
 
 def sigma_vec():
@@ -57,6 +84,34 @@ def init_positions(n, rank, sigma):
     """q0 = sigma * z: exact draws from the target, so ESS is measured at stationarity."""
     rng = np.random.Generator(np.random.Philox(key=SEED + 7919 * rank))
     return rng.standard_normal((n, D)) * sigma
+
+
+def make_inputs(spec, n, rank):
+    """(q0 [n, d], data) of a workload; states start in the typical set."""
+    rng = np.random.Generator(np.random.Philox(key=SEED + 7919 * rank + 13))
+    t = spec["target"]
+    if t == "diag_gauss":
+        sigma = sigma_vec()
+        return init_positions(n, rank, sigma), {"inv_var": 1.0 / sigma ** 2}
+    if t == "std_normal":
+        q0 = rng.standard_normal((n, spec["d"]))
+        return q0, ({"inv_mass": np.ones(spec["d"])} if spec["mode"] == "package" else {})
+    if t == "funnel":
+        q0 = np.empty((n, 11))
+        q0[:, 0] = 3.0 * rng.standard_normal(n)
+        q0[:, 1:] = np.exp(0.5 * q0[:, :1]) * rng.standard_normal((n, 10))
+        return q0, {}
+    if t == "logreg":
+        from walnuts_b200 import datasets
+        X, y, beta = datasets.synth_logreg(100_000, 100, 0)
+        return beta + 0.05 * rng.standard_normal((n, 100)), {"X": X, "y": y, "tau": np.array([1.0])}
+    if t == "stock_watson":
+        from walnuts_b200 import datasets
+        y = datasets.stock_watson_series()
+        q0 = 0.05 * rng.standard_normal((n, 3 * y.size))
+        q0[:, 0] = 2.4
+        return q0, {"y": y}
+    raise KeyError(t)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -80,6 +135,7 @@ class ClockSampler:
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
             self.proc = None
+        return self
 
     def _pump(self):
         for line in self.proc.stdout:
@@ -101,250 +157,431 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------------
-# CPU baseline: the numpy restatement of the reference, one chain per process on every host core
+# CPU arm: the numpy restatement of the reference (oracle/), one chain per process on every host core.  The only
+# place besides tests/ and smoke() that executes anything under oracle/ (as the baseline being timed).
 # --------------------------------------------------------------------------------------------------
-def _cpu_chain(args):
-    chain, iters = args
+def _cpu_worker(args):
+    """Run transitions of chain `chain` of workload `name` for ~`budget` seconds (at least `min_tr` timed
+    transitions after `warm` untimed ones, at most `max_tr`).  Returns (evals, seconds, transitions)."""
+    name, chain, budget, min_tr, max_tr, warm = args
     os.environ["OMP_NUM_THREADS"] = "1"
+    spec = WORKLOADS[name]
+    q0, data = make_inputs(spec, chain + 1, 0)
+    q = q0[chain]
     from oracle import targets as ot
-    from oracle import walnutspy_oracle as wo
-    sigma = sigma_vec()
-    lp = ot.make_diag_gauss(sigma)
-    q0 = init_positions(chain + 1, 0, sigma)[chain]
-    t0 = time.perf_counter()
+    evals, n_tr, t_used = 0.0, 0, 0.0
     with np.errstate(all="ignore"):
-        s, dg = wo.WALNUTS(lp, q0, integrator=wo.ADAPT_R2P, H0=CFG["H0"], delta0=CFG["delta"], numIter=iters,
-                           M=CFG["M"], igrAux=wo.AuxPar(CFG["minC"], CFG["maxC"]), seed=SEED, chain=chain)
-    dt = time.perf_counter() - t0
-    return float(dg[:, 6].sum() + dg[:, 7].sum()), dt
+        if spec["mode"] == "package":
+            from oracle import package_oracle as po
+            it = 1
+            while True:
+                cnt = [0]
+                t0 = time.perf_counter()
+                q = po.walnuts(SEED, chain, q, ot.standard_normal_lpdf, ot.standard_normal_grad, data["inv_mass"],
+                               spec["H0"], spec["M"], spec["delta"], 0, 1, first_iteration=it, counter=cnt)[-1]
+                dt = time.perf_counter() - t0
+                it += 1
+                if it - 1 > warm:
+                    evals += cnt[0]; t_used += dt; n_tr += 1
+                    if (t_used >= budget and n_tr >= min_tr) or n_tr >= max_tr:
+                        break
+            return evals, t_used, n_tr
+        from oracle import walnutspy_oracle as wo
+        t = spec["target"]
+        if t == "diag_gauss":
+            lp = ot.make_diag_gauss(1.0 / np.sqrt(data["inv_var"]))
+        elif t == "funnel":
+            lp = ot.funnel10
+        elif t == "logreg":
+            lp = ot.make_logreg(data["X"], data["y"], 1.0)
+        elif t == "stock_watson":
+            lp = ot.make_stock_watson(data["y"])
+        else:
+            lp = ot.std_normal
+        kind = {"fixed": wo.FIXED, "D": wo.ADAPT_D, "R2P": wo.ADAPT_R2P}[spec["integrator"]]
+        it = 1
+        while True:
+            t0 = time.perf_counter()
+            s, dg = wo.WALNUTS(lp, q, integrator=kind, H0=spec["H0"], delta0=spec["delta"], numIter=1, M=spec["M"],
+                               igrAux=wo.AuxPar(spec["minC"], spec["maxC"]), seed=SEED, chain=chain, first_iteration=it)
+            dt = time.perf_counter() - t0
+            q = s[:, -1]
+            it += 1
+            if it - 1 > warm:
+                evals += float(dg[:, 6].sum() + dg[:, 7].sum()); t_used += dt; n_tr += 1
+                if (t_used >= budget and n_tr >= min_tr) or n_tr >= max_tr:
+                    break
+    return evals, t_used, n_tr
 
 
-def cpu_baseline(iters=1, cores=None):
-    """Gradient evals/sec of the reference algorithm (numpy port) on all host cores."""
-    import multiprocessing as mp
+_POOL = None
+
+
+def _pool(cores):
+    global _POOL
+    if _POOL is None:
+        import multiprocessing as mp
+        _POOL = mp.get_context("spawn").Pool(cores)
+    return _POOL
+
+
+def cpu_baseline(name="c2", budget=12.0, min_tr=1, max_tr=10 ** 9, warm=0, cores=None):
+    """Gradient evals/sec of the reference algorithm (numpy port) with every host core busy on its own chain:
+    the sum over cores of (evaluations / busy seconds)."""
     cores = cores or os.cpu_count() or 1
-    ctx = mp.get_context("spawn")
     t0 = time.perf_counter()
-    with ctx.Pool(cores) as pool:
-        res = pool.map(_cpu_chain, [(c, iters) for c in range(cores)])
+    res = _pool(cores).map(_cpu_worker, [(name, c, budget, min_tr, max_tr, warm) for c in range(cores)])
     wall = time.perf_counter() - t0
-    evals = sum(r[0] for r in res)
-    busy = max(r[1] for r in res)
-    return {"value": evals / busy, "unit": "grad_evals/s", "cores": cores, "kind": "port",
-            "sample": f"{cores} chains x {iters} transition(s) of the bench workload, one chain per process "
-                      f"(numpy restatement of WALNUTSpy; {evals:.0f} evals in {busy:.1f}s, wall {wall:.1f}s)",
-            "per_core": evals / busy / cores, "seconds": busy}
+    rate = sum(r[0] / r[1] for r in res)
+    n_tr = [r[2] for r in res]
+    return {"value": rate, "unit": "grad_evals/s", "cores": cores, "kind": "port",
+            "sample": f"{cores} chains (one per process, OMP_NUM_THREADS=1) x {min(n_tr)}..{max(n_tr)} transitions of "
+                      f"{WORKLOADS[name]['workload']} on the numpy restatement of the reference "
+                      f"({sum(r[0] for r in res):.0f} evals, {max(r[1] for r in res):.1f}s busy, wall {wall:.1f}s)",
+            "per_core": rate / cores, "transitions_min": min(n_tr), "seconds": float(np.mean([r[1] for r in res])),
+            "seconds_per_transition": float(np.mean([r[1] / r[2] for r in res]))}
 
 
-def cpu_baseline_c(iters=1, cores=None, chains_per_core=4):
-    """The same workload on the C restatement (oracle/c/walnuts_oracle.c, -O3, pthreads): the strong CPU
-    baseline standing in for the absent walnuts_cpp."""
+def cpu_baseline_c(seconds=6.0, cores=None, ess=False):
+    """C2 on the C restatement (oracle/c/walnuts_oracle.c, gcc -O3, pthreads): the strong CPU baseline standing in
+    for the absent walnuts_cpp.  ess=True: keep going for `seconds` and measure the bulk ESS of the CPU draws."""
     from oracle import c_oracle
+    from walnuts_b200 import diagnostics
     cores = cores or os.cpu_count() or 1
     sigma = sigma_vec()
-    n = cores * chains_per_core
+    n = cores
     q = np.ascontiguousarray(init_positions(n, 0, sigma))
+    draws, evals, it = [], 0, 1
     t0 = time.perf_counter()
-    evals = c_oracle.run_many("diag_gauss", "R2P", q, CFG["H0"], CFG["delta"], CFG["M"], iters, SEED, cores,
-                              minC=CFG["minC"], maxC=CFG["maxC"], inv_var=1.0 / sigma ** 2, jitter=CFG["jitter"])
+    while True:
+        evals += c_oracle.run_many("diag_gauss", "R2P", q, 0.5, 0.3, 10, 1, SEED, cores, minC=0, maxC=10,
+                                   inv_var=1.0 / sigma ** 2, jitter=0.2, first_iteration=it)
+        it += 1
+        draws.append(q[:, :MONITOR].copy())
+        if time.perf_counter() - t0 >= seconds and len(draws) >= 4:
+            break
     dt = time.perf_counter() - t0
-    return {"value": evals / dt, "unit": "grad_evals/s", "cores": cores, "kind": "port-c",
-            "sample": f"{n} chains x {iters} transition(s) on {cores} pthreads (C restatement, gcc -O3 -mavx2; "
-                      f"{evals} evals in {dt:.1f}s)", "per_core": evals / dt / cores}
+    out = {"value": evals / dt, "unit": "grad_evals/s", "cores": cores, "kind": "port-c",
+           "sample": f"{n} chains x {len(draws)} transitions on {cores} pthreads (C restatement of the transition, "
+                     f"gcc -O3; {evals} evals in {dt:.1f}s)", "per_core": evals / dt / cores}
+    if ess:
+        x = np.stack(draws)                                   # (draws, chains, monitor)
+        vals = [diagnostics.ess_bulk(x[:, :, j].T)[0] for j in range(MONITOR)]
+        out.update(min_ess=float(np.nanmin(vals)), min_ess_per_sec=float(np.nanmin(vals)) / dt,
+                   ess_draws_per_chain=len(draws), ess_chains=n,
+                   ess_note="bulk ESS of the CPU arm's OWN draws (few draws per chain: a noisy estimate)")
+    return out
 
 
 # --------------------------------------------------------------------------------------------------
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=4)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--iters", type=int, default=2, help="transitions per chain per step")
-    ap.add_argument("--chains", type=int, default=CHAINS_PER_GPU, help="chains per GPU")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--cpu-iters", type=int, default=1)
-    args = ap.parse_args()
+# GPU legs
+# --------------------------------------------------------------------------------------------------
+class Env:
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            torch.cuda.set_device(self.local_rank)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+        self.dev = torch.device("cuda", self.local_rank)
+        torch.cuda.set_device(self.dev)
+        self.flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)   # 2 x the 126 MB L2
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    config = {"workload": "diag_gauss_d1000_sigma_logspace(-2,2)_R2P", "chains_per_gpu": args.chains,
-              "d": D, "iters_per_step": args.iters, **CFG,
-              "l2_policy": "per-step working set (positions 524 MB + scratch) exceeds the 126 MB L2"}
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    if args.impl == "reference":
-        if rank != 0:
-            return
-        cb = None
-        vals, secs = [], []
-        for _ in range(max(1, min(args.steps, 3))):
-            cb = cpu_baseline(args.cpu_iters)
-            vals.append(cb["value"])
-            secs.append(cb["seconds"])
-        cb["value"] = float(np.mean(vals))
-        try:
-            extra_c = cpu_baseline_c(args.cpu_iters)
-        except Exception as e:
-            extra_c = {"unavailable": str(e)[:200]}
-        line = {"impl": "reference", "cpu_baseline_c": extra_c, "metric": "grad_evals_per_sec", "value": cb["value"], "unit": "grad_evals/s",
-                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": 1e3 * float(np.mean(secs)),     # one step = the bounded sample described in cpu_baseline
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-                "data": "synthetic", "config": config, "cpu_baseline": cb,
-                "e2e": {"value": cb["value"], "unit": "grad_evals/s", "h2d_bytes_per_step": 0,
-                        "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
-        return
+    def flush_l2(self):
+        self.flush_buf.zero_()
 
-    import torch
-    import torch.distributed as dist
-    from walnuts_b200 import ChainBatch, diagnostics, fp64_peak, _ffi
+    def reduce(self, maxes, sums):
+        t = self.torch
+        a = t.tensor(maxes, dtype=t.float64, device=self.dev)
+        b = t.tensor(sums, dtype=t.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(a, op=self.dist.ReduceOp.MAX)
+            self.dist.all_reduce(b, op=self.dist.ReduceOp.SUM)
+        return [float(x) for x in a], [float(x) for x in b]
 
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    dev = torch.device("cuda", local_rank)
-    torch.cuda.set_device(dev)
 
-    sigma = sigma_vec()
-    n = args.chains
-    q0 = init_positions(n, rank, sigma)
-    cb = ChainBatch("diag_gauss", D, n, integrator=CFG["integrator"], H0=CFG["H0"], jitter=CFG["jitter"],
-                    delta=CFG["delta"], M=CFG["M"], minC=CFG["minC"], maxC=CFG["maxC"], seed=SEED,
-                    chain_offset=rank * n, device=local_rank, dg=MONITOR, data={"inv_var": 1.0 / sigma ** 2})
+def make_batch(spec, n, chain_offset, device, data, q0):
+    from walnuts_b200 import ChainBatch
+    cb = ChainBatch(spec["target"], spec["d"], n, mode=spec["mode"], integrator=spec["integrator"], H0=spec["H0"],
+                    jitter=0.2, delta=spec["delta"], M=spec["M"], minC=spec["minC"], maxC=spec["maxC"], seed=SEED,
+                    chain_offset=chain_offset, device=device, dg=spec["monitor"], data=data)
     cb.set_state(q0)
+    return cb
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
-    # ---- device-resident timing ------------------------------------------------------------------
-    total_iters = args.iters * args.steps
-    draws = torch.empty((total_iters, n, MONITOR), dtype=torch.float64, device=dev)
-    for _ in range(args.warmup):
-        cb.run_device(args.iters, draws=draws[:args.iters])
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    t0 = time.perf_counter()
+def gpu_leg(env, name, steps, warmup, chains=None, e2e=True, fp64_peak=None, keep_draws=False):
+    """Device-resident timing (+ e2e through pinned host buffers) of one workload; returns the reduced dict on
+    every rank."""
+    from walnuts_b200.sampler import pinned_empty
+    torch = env.torch
+    spec = WORKLOADS[name]
+    n = chains or spec["chains"]
+    iters, mon, pkg = spec["iters"], spec["monitor"], spec["mode"] == "package"
+    q0, data = make_inputs(spec, n, env.rank)
+    cb = make_batch(spec, n, env.rank * n, env.local_rank, data, q0)
+    draws = torch.empty((iters, n, mon), dtype=torch.float64, device=env.dev)
+    for _ in range(warmup):
+        cb.run_device(iters, draws=draws)
+    env.barrier()
+    sampler = ClockSampler(env.local_rank).start() if env.rank == 0 else None
     kernel_ms, evals = [], 0
-    for s in range(args.steps):
-        cb.run_device(args.iters, draws=draws[s * args.iters:(s + 1) * args.iters], sync=False)
-        cb.sync()
+    for s in range(steps):
+        env.flush_l2()
+        cb.run_device(iters, draws=draws)
         kernel_ms.append(cb.last_kernel_ms())
         f, b = cb.last_grad_evals()
         evals += f + b
-    barrier()
-    wall = time.perf_counter() - t0
-    clocks = sampler.stop() if rank == 0 else None
+    env.barrier()
+    clocks = sampler.stop() if sampler else None
+    launches = steps * cb.last_launches()
     dev_ms = float(sum(kernel_ms))
 
-    # ---- e2e: host buffers through the public API ------------------------------------------------
-    host_q = torch.empty((n, D), dtype=torch.float64).pin_memory()
-    cb.get_state(host_q.numpy())
-    e2e_evals = 0
-    barrier()
-    t1 = time.perf_counter()
-    h2d = d2h = 0
-    for s in range(args.steps):
-        cb.set_state(host_q.numpy())
-        out = cb.run(args.iters, draws=True, diag=True)
-        cb.get_state(host_q.numpy())
-        f, b = cb.last_grad_evals()
-        e2e_evals += f + b
-        h2d = host_q.numel() * 8
-        d2h = out["draws"].nbytes + out["diag"].nbytes + out["nevalF"].nbytes + out["nevalB"].nbytes + host_q.numel() * 8
-    barrier()
-    e2e_wall = time.perf_counter() - t1
+    # ---- e2e: the same steps through HOST buffers, copies inside the timed region; the chains are split over two
+    # handles so that the copies of one half overlap the kernel of the other -------------------------------------
+    e2e_wall, e2e_evals, h2d, d2h = 0.0, 0, 0, 0
+    if e2e and spec.get("e2e", True):
+        state = cb.get_state()
+        cb.close()
+        halves = [(0, n // 2), (n // 2, n - n // 2)] if n >= 2 else [(0, n)]
+        hs = []
+        for off, m in halves:
+            h = make_batch(spec, m, env.rank * n + off, env.local_rank, data, state[off:off + m])
+            bufs = dict(q=pinned_empty((m, spec["d"])), dr=pinned_empty((iters, m, mon)),
+                        dg=None if pkg else pinned_empty((iters, m, 24)),
+                        f=pinned_empty((m,), np.uint64), b=None if pkg else pinned_empty((m,), np.uint64))
+            bufs["q"][:] = state[off:off + m]
+            hs.append((h, bufs))
+        del state
 
-    # ---- reduce over ranks -----------------------------------------------------------------------
-    stats = torch.tensor([dev_ms, wall, e2e_wall], dtype=torch.float64, device=dev)
-    sums = torch.tensor([float(evals), float(e2e_evals)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
-        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-    dev_ms_max, wall_max, e2e_wall_max = [float(x) for x in stats]
-    evals_all, e2e_evals_all = [float(x) for x in sums]
+        def enqueue(h, bf):
+            h.run_host_async(iters, q_in=bf["q"], draws=bf["dr"], diag=bf["dg"], nevalF=bf["f"], nevalB=bf["b"],
+                             q_out=bf["q"])
 
-    # ---- min-ESS over the monitored coordinates (cross-chain, one small reduction over NVLink) ------
-    ess_vals = []
-    for j in range(MONITOR):
-        z = draws[:, :, j].t().contiguous()
-        st = diagnostics.chain_stats(z, max_lag=min(total_iters - 1, 32))
-        vec = torch.stack([torch.as_tensor(float(st["m"]), device=dev, dtype=torch.float64), st["sum_mean"],
-                           st["sum_mean2"], st["sum_var"], *st["acov_sum"]])
-        if world > 1:
-            dist.all_reduce(vec, op=dist.ReduceOp.SUM)
-        vec = vec.cpu().numpy()
-        st2 = dict(m=vec[0], n=total_iters, sum_mean=vec[1], sum_mean2=vec[2], sum_var=vec[3], acov_sum=vec[4:])
-        ess_vals.append(diagnostics.ess_from_stats(st2)[0])
-    min_ess = float(np.nanmin(ess_vals)) if total_iters >= 4 else None
+        def finish(h):
+            h.sync()                                          # this half's results are in its host buffers now
+            f, b = h.last_grad_evals()
+            return f + b
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        def run_steps(k):
+            # handle-level software pipeline: a half is re-enqueued as soon as ITS results of the previous step have
+            # arrived, while the other half's kernel is still running
+            tot = 0
+            for h, bf in hs:
+                enqueue(h, bf)
+            for s in range(1, k):
+                for h, bf in hs:
+                    tot += finish(h)
+                    enqueue(h, bf)
+            for h, bf in hs:
+                tot += finish(h)
+            return tot
+        run_steps(1)                                          # staging buffers / scratch allocated outside the timing
+        env.barrier()
+        t1 = time.perf_counter()
+        e2e_evals = run_steps(steps)
+        env.barrier()
+        e2e_wall = time.perf_counter() - t1
+        for h, bf in hs:
+            h2d += bf["q"].nbytes
+            d2h += sum(x.nbytes for x in bf.values() if x is not None)
+            h.close()
+    else:
+        cb.close()
+
+    (dev_ms_max, e2e_wall_max), (evals_all, e2e_evals_all) = env.reduce([dev_ms, e2e_wall], [float(evals), float(e2e_evals)])
+    value = evals_all / (dev_ms_max * 1e-3)
+    per_launch_flops = spec["flop_per_eval"] * (evals / max(1, steps))
+    ach = per_launch_flops / (np.mean(kernel_ms) * 1e-3) / 1e12
+    out = {"workload": spec["workload"], "value": value, "unit": "grad_evals/s", "steps": steps, "warmup": warmup,
+           "ms_per_step": dev_ms_max / max(1, steps), "chains_per_gpu": n, "chains_total": n * env.world,
+           "iters_per_step": iters, "evals_per_transition": evals_all / (steps * iters * n * env.world),
+           "gpu_launches": launches, "clocks": clocks,
+           "params": {k: spec[k] for k in ("integrator", "H0", "delta", "M", "minC", "maxC", "mode")},
+           "roofline": {"bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
+                        "frac": (ach / fp64_peak) if fp64_peak else None, "flop_per_eval": spec["flop_per_eval"],
+                        "traffic": None,
+                        "note": "achieved = SURVEY.md 8(d) algorithmic flop per gradient evaluation x evaluations of one "
+                                "launch / its CUDA-event duration; peak = FP64 FMA micro-benchmark of this run "
+                                "(MEASURED_PEAKS.json has no FP64 entry); register-resident chains: not HBM-bound"}}
+    if e2e_wall_max > 0:
+        out["e2e"] = {"value": e2e_evals_all / e2e_wall_max, "unit": "grad_evals/s", "h2d_bytes_per_step": h2d,
+                      "d2h_bytes_per_step": d2h, "handles_per_gpu": len(halves)}
+    if keep_draws:
+        out["_draws"] = draws
+    return out
+
+
+def ess_leg(env, chains=ESS_CHAINS, n_draws=ESS_DRAWS):
+    """min-ESS/sec: `chains` chains per GPU x `n_draws` transitions of the headline workload in ONE launch; bulk ESS
+    (rank-normalised, split chains) and split-R-hat over ALL chains of all GPUs after one all-gather of the
+    monitored draws."""
+    from walnuts_b200 import diagnostics
+    torch = env.torch
+    spec = WORKLOADS["c2"]
+    q0, data = make_inputs(spec, chains, env.rank)
+    cb = make_batch(spec, chains, (1 << 24) + env.rank * chains, env.local_rank, data, q0)
+    draws = torch.empty((n_draws, chains, MONITOR), dtype=torch.float64, device=env.dev)
+    env.barrier()
+    cb.run_device(n_draws, draws=draws)
+    ms = cb.last_kernel_ms()
+    f, b = cb.last_grad_evals()
+    cb.close()
+    env.barrier()
+    (ms_max,), (evals_all,) = env.reduce([ms], [float(f + b)])
+    if env.world > 1:
+        parts = [torch.empty_like(draws) for _ in range(env.world)]
+        env.dist.all_gather(parts, draws)                      # the one collective: monitored draws over NVLink
+        draws = torch.cat(parts, 1)
+    per, rh = [], []
+    if env.rank == 0:
+        for j in range(MONITOR):
+            e, r = diagnostics.ess_bulk(draws[:, :, j].t().contiguous())
+            per.append(float(e)); rh.append(float(r))
+    sig = sigma_vec()[:MONITOR]
+    if env.rank != 0:
+        return None
+    k = int(np.nanargmin(per))
+    total = chains * env.world * n_draws
+    return {"chains_total": chains * env.world, "draws_per_chain": n_draws, "seconds": ms_max * 1e-3,
+            "grad_evals": evals_all, "min_ess": per[k], "min_ess_per_sec": per[k] / (ms_max * 1e-3),
+            "min_ess_per_grad_eval": per[k] / evals_all, "slowest_sigma": float(sig[k]),
+            "tau_max_draws": total / per[k], "split_chain_length": n_draws // 2, "rhat_max": float(np.nanmax(rh)),
+            "ess_per_coordinate": per, "rhat_per_coordinate": rh, "sigma_monitored": [float(x) for x in sig],
+            "estimator": "bulk ESS: rank-normalised, split chains, Geyer initial monotone sequence on chain-averaged "
+                         "autocorrelations with all lags available (Vehtari et al. 2021 = arviz.ess default, "
+                         "mainGaussESS.py:50-55); chains start from exact draws of the target"}
+
+
+# --------------------------------------------------------------------------------------------------
+def reference_arm(args):
+    """The reference's own CPU implementation of the path (numpy restatement) on all host cores, headline workload.
+    Every core advances its own chain: `warmup` untimed transitions (capped at 1), then timed transitions until the
+    time budget is used (at least 4, at most --steps).  One step = one transition of every core's chain; `steps` is
+    the number actually executed by every core."""
+    cb = cpu_baseline("c2", budget=args.ref_budget, min_tr=4, max_tr=max(4, args.steps), warm=min(1, args.warmup))
+    try:
+        extra_c = cpu_baseline_c(6.0)
+    except Exception as e:
+        extra_c = {"unavailable": str(e)[:200]}
+    spec = WORKLOADS["c2"]
+    config = {"workload": spec["workload"], "chains": cb["cores"], "d": D,
+              **{k: spec[k] for k in ("integrator", "H0", "delta", "M", "minC", "maxC")}, "jitter": 0.2}
+    line = {"impl": "reference", "metric": "grad_evals_per_sec", "value": cb["value"], "unit": "grad_evals/s",
+            "n_gpus": args.gpus, "steps": cb["transitions_min"], "warmup": min(1, args.warmup),
+            "steps_requested": args.steps, "ms_per_step": 1e3 * cb["seconds_per_transition"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config, "cpu_baseline": cb, "cpu_baseline_c": extra_c,
+            "e2e": {"value": cb["value"], "unit": "grad_evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--chains", type=int, default=CHAINS_PER_GPU, help="headline chains per GPU")
+    ap.add_argument("--configs", default="all", help="'all', 'none' or a comma list of " + ",".join(CONFIG_ORDER))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
+    ap.add_argument("--no-ess", action="store_true", help="skip the min-ESS/sec leg")
+    ap.add_argument("--ess-chains", type=int, default=ESS_CHAINS)
+    ap.add_argument("--ess-draws", type=int, default=ESS_DRAWS)
+    ap.add_argument("--ref-budget", type=float, default=60.0, help="seconds per core of the reference arm")
+    args = ap.parse_args()
+
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) == 0:
+            reference_arm(args)
         return
 
-    value = evals_all / (dev_ms_max * 1e-3)
-    flops = FLOP_PER_DIM_PER_EVAL * D * (evals / max(1, args.steps))       # per launch (this rank)
-    ach = flops / (np.mean(kernel_ms) * 1e-3) / 1e12
+    env = Env()
+    from walnuts_b200 import _ffi, fp64_peak
     try:
-        peak = fp64_peak(local_rank) / 1e12
+        peak = fp64_peak(env.local_rank) / 1e12
         peak_src = "measured FP64 FMA micro-benchmark (wn_fp64_peak) on this GPU, this run"
     except Exception:
         peak, peak_src = 148 * 64 * 2 * 1.965e9 / 1e12, "nominal 148 SM x 64 FMA/clk x 1.965 GHz (fallback)"
+
+    head = gpu_leg(env, "c2", args.steps, args.warmup, chains=args.chains, fp64_peak=peak)
+    names = CONFIG_ORDER if args.configs == "all" else ([] if args.configs == "none" else args.configs.split(","))
+    configs = {}
+    for name in names:
+        spec = WORKLOADS[name]
+        if spec.get("single_gpu_only") and env.world > 1:
+            continue
+        configs[name] = gpu_leg(env, name, max(1, min(args.steps, spec["steps_cap"])), min(args.warmup, spec["warmup_cap"]),
+                                fp64_peak=peak)
+    strong = None
+    if env.world > 1:
+        st = gpu_leg(env, "c2", min(args.steps, 5), min(args.warmup, 3), chains=CHAINS_PER_GPU // env.world, e2e=False,
+                     fp64_peak=peak)
+        strong = {k: st[k] for k in ("value", "unit", "ms_per_step", "steps", "warmup", "chains_per_gpu", "chains_total")}
+        strong["note"] = "strong scaling: the headline workload with 65 536 chains in TOTAL"
+    ess = None if args.no_ess else ess_leg(env, args.ess_chains, args.ess_draws)
+    if env.rank != 0:
+        if env.world > 1:
+            env.dist.destroy_process_group()
+        return
+
     try:
         hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
     except Exception:
         hbm_peak = 6650.0
+    spec = WORKLOADS["c2"]
+    roof = head["roofline"]
+    # C2 / R2P: the kernel EXECUTES 4 flop per coordinate and gradient evaluation (merged kicks, linear gradient folded
+    # into the kick, energies only where they are consumed: DESIGN.md section 6) against the 12 of SURVEY.md 8(d);
+    # `frac` is the executed work over the measured peak, the 12-flop figure is reported next to it
+    roof.update(achieved=roof["achieved"] * 4.0 / 12.0, frac=roof["frac"] * 4.0 / 12.0, flop_per_eval=4.0 * D,
+                achieved_at_12_flop_per_coord=roof["achieved"], frac_at_12_flop_per_coord=roof["frac"],
+                peak_source=peak_src,
+                hbm={"streaming_model_gbs": head["value"] / env.world * 48 * D / 1e9, "peak_gbs": hbm_peak,
+                     "note": "SURVEY.md 8(d) streaming model (48 d bytes per evaluation if q, v, g went through HBM every "
+                             "micro-step) vs the measured HBM peak: the chains are register-resident, HBM is not the bound"})
     line = {
-        "metric": "grad_evals_per_sec", "value": value, "unit": "grad_evals/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
+        "metric": "grad_evals_per_sec", "value": head["value"], "unit": "grad_evals/s", "n_gpus": env.world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": head["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": config,
-        "min_ess_per_sec": (min_ess / (dev_ms_max * 1e-3)) if min_ess else None,
-        "min_ess": min_ess, "grad_evals": evals_all, "wall_s": wall_max,
-        "e2e": {"value": e2e_evals_all / e2e_wall_max, "unit": "grad_evals/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h},
-        "gpu_launches": args.steps * cb.last_launches(),
-        "clocks": clocks,
-        "roofline": {"bound": "fp64", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                     # dram__bytes_read+write of one `ncu --set full` launch (0.170 + 0.768 GB for 3.206e8 evaluations,
-                     # profiles/r01_walnutspy_diag1000_R2P.txt), scaled to the evaluations of one bench launch
-                     "traffic": 0.938e9 * (evals / max(1, args.steps)) / 3.206e8,
-                     "flop_per_eval": FLOP_PER_DIM_PER_EVAL * D,
-                     "achieved_at_8_flop_per_coord": ach * 8 / FLOP_PER_DIM_PER_EVAL,
-                     "achieved_at_12_flop_per_coord": ach * 12 / FLOP_PER_DIM_PER_EVAL,
-                     "peak_source": peak_src,
-                     # SURVEY.md 8(d) streaming model: 48 d bytes per evaluation if (q, v, g) were re-read and
-                     # re-written every micro-step; what HBM would have to deliver at the measured rate
-                     "hbm": {"streaming_model_gbs": value / max(1, world) * 48 * D / 1e9, "peak_gbs": hbm_peak,
-                             "streaming_model_over_peak": value / max(1, world) * 48 * D / 1e9 / hbm_peak},
-                     "note": "register-resident chains: FP64 FMA pipe bound, not HBM (SURVEY.md 8d); "
-                             f"HBM peak {hbm_peak} GB/s is not the limiter"},
-        "lib": os.path.relpath(_ffi.lib_path(), ROOT),
+        "config": {"workload": spec["workload"], "chains_per_gpu": args.chains, "d": D, "iters_per_step": spec["iters"],
+                   **{k: spec[k] for k in ("integrator", "H0", "delta", "M", "minC", "maxC")}, "jitter": 0.2,
+                   "l2_policy": "a 256 MB buffer is overwritten between timed steps (2 x the 126 MB L2); the headline's "
+                                "positions alone are 524 MB"},
+        "evals_per_transition": head["evals_per_transition"],
+        "e2e": head.get("e2e"), "gpu_launches": head["gpu_launches"], "clocks": head["clocks"], "roofline": roof,
+        "min_ess_per_sec": ess["min_ess_per_sec"] if ess else None, "ess": ess,
+        "configs": configs, "strong_scaling": strong, "lib": os.path.relpath(_ffi.lib_path(), ROOT),
     }
-    if world == 1 and not args.no_cpu:
-        line["cpu_baseline"] = cpu_baseline(args.cpu_iters)
-        if min_ess:
-            # identical transition kernel on identical streams (parity tests) => identical ESS per gradient
-            # evaluation; the CPU's min-ESS/sec is therefore its evals/s times the measured ESS per evaluation
-            per_eval = min_ess / evals_all
-            line["min_ess_per_grad_eval"] = per_eval
-            line["cpu_baseline"]["min_ess_per_sec"] = per_eval * line["cpu_baseline"]["value"]
+    if env.world == 1 and not args.no_cpu:
+        line["cpu_baseline"] = cpu_baseline("c2", budget=12.0, min_tr=1)
+        budgets = {"c1": 3.0, "c2_nuts": 4.0, "c3": 4.0, "c4": 8.0, "c5": 5.0}
+        for name, c in configs.items():
+            if name in budgets:
+                try:
+                    c["cpu_baseline"] = cpu_baseline(name, budget=budgets[name], min_tr=1)
+                except Exception as e:                            # a failed CPU leg must not lose the GPU numbers
+                    c["cpu_baseline"] = {"unavailable": str(e)[:200]}
         try:
-            line["cpu_baseline_c"] = cpu_baseline_c(args.cpu_iters)
-            if min_ess:
-                line["cpu_baseline_c"]["min_ess_per_sec"] = min_ess / evals_all * line["cpu_baseline_c"]["value"]
-        except Exception as e:                                   # the C checker is optional for the bench
+            line["cpu_baseline_c"] = cpu_baseline_c(20.0 if ess else 6.0, ess=bool(ess))
+        except Exception as e:                                    # the C checker is optional for the bench
             line["cpu_baseline_c"] = {"unavailable": str(e)[:200]}
+        if ess:
+            # the CPU arm runs the identical transition kernel on identical streams (parity tests), so its ESS per
+            # gradient evaluation is the GPU leg's; derived figure, next to the one measured on the C port's own draws
+            line["cpu_baseline"]["min_ess_per_sec_derived"] = ess["min_ess_per_grad_eval"] * line["cpu_baseline"]["value"]
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    if env.world > 1:
+        env.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -84,7 +84,9 @@ typedef struct wn_config {
   int32_t compat;      /* 1 = reproduce the reference's latent defects bit-for-bit: PACKAGE mode B3/B5
                           (walnuts.py:194,242-245,272), WALNUTSPY mode A14(i) (WALNUTS.py:420 vs :443-459,
                           biases the funnel); 0 = corrected semantics           */
-  int32_t reserved0;
+  int32_t first_iteration; /* iteration number of the handle's first transition in the Philox counters; 0 or 1 = start
+                          at 1 (WALNUTS.py:196 counts from 1).  A caller that creates a fresh handle per transition with
+                          a FIXED seed (walnuts_step) must advance this, or every call replays the same streams */
   double H0;           /* macro step: WALNUTS(H0=) / walnuts(macro_step=)                */
   double jitter;       /* WALNUTS(stepSizeRandScale=), WALNUTS.py:298,395                */
   double delta;        /* WALNUTS(delta0=) / walnuts(max_error=)                         */
@@ -104,7 +106,7 @@ int wn_target_id(const char* name);
 /* Load a user-target plug-in (built by walnuts_b200.targets.cuda_target() from csrc/wn_user_api.cuh, the user's
  * WN_TARGET_LP_GRAD function and csrc/wn_user_plugin.cuh) and return its target id (>= WN_TARGET_USER_BASE),
  * or <0.  The plug-in fixes the dimension d; its data array travels with wn_set_data(h, "data", ...).
- * The registry is process-wide and append-only (plug-ins stay loaded); call it from one thread at a time. */
+ * The registry is process-wide and append-only (plug-ins stay loaded); registration is serialised internally. */
 int wn_register_user_target(const char* plugin_path);
 
 int wn_create(const wn_config* cfg, wn_handle** out);
@@ -152,6 +154,19 @@ int wn_run_stats(wn_handle* h, int64_t n_iter, double* draws, double* diag, uint
 int wn_run_async(wn_handle* h, int64_t n_iter, double* d_draws, double* d_diag,
                  uint64_t* d_nevalF, uint64_t* d_nevalB);
 int wn_sync(wn_handle* h);
+
+/* The whole step with HOST buffers, asynchronous on the handle's stream: copy `q_in` [n_chains, d] to the device
+ * (NULL: keep the current positions), run n_iter transitions, copy draws / diag / nevalF / nevalB (each may be
+ * NULL) and the final positions `q_out` [n_chains, d] (may be NULL) back.  Every buffer is host memory; buffers
+ * from wn_alloc_pinned() make the copies truly asynchronous, so that two handles on one device overlap the
+ * copies of one with the kernel of the other.  Pair with wn_sync().  This is the host-buffer form of the
+ * reference's per-call contract (caller-owned numpy arrays in, fresh arrays out: WALNUTS.py:111,724-727). */
+int wn_run_host_async(wn_handle* h, int64_t n_iter, const double* q_in, double* draws, double* diag,
+                      uint64_t* nevalF, uint64_t* nevalB, double* q_out);
+
+/* page-locked host memory for the asynchronous host-buffer path */
+int wn_alloc_pinned(int64_t bytes, void** out);
+int wn_free_pinned(void* p);
 
 /* Device time of the last wn_run / wn_run_async kernel in milliseconds (CUDA events on the
  * handle's stream), its launch count, and the total gradient evaluations it performed. */

@@ -7,12 +7,39 @@ from oracle import walnutspy_oracle as wo
 RTOL = 1e-10   # north_star: per-iteration draws match in fp64 to 1e-10 relative error
 
 
-def close(a, b, rtol=RTOL):
+def close(a, b, rtol=RTOL, scale=None, axis=-1):
+    """TRUE relative agreement, coordinate by coordinate: |a - b| <= rtol * scale_j.
+
+    `axis` is the coordinate axis.  scale=None: scale_j = the largest |b| of coordinate j over all other axes
+    (iterations, chains) -- the coordinate's own magnitude, a stand-in for its standard deviation, so that a
+    small-sigma coordinate is held to 1e-10 of ITS size (the round-1 harness used max(1, |b|), an absolute
+    tolerance for everything below 1) while a value that happens to pass through zero is not held to an impossible
+    standard.  Pass `scale` (broadcastable, e.g. sigma) to fix the scales.  Coordinates that are identically zero
+    get a floor of 1e-6 of the overall magnitude.  Returns (ok, worst relative error)."""
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
-    scale = np.maximum(1.0, np.abs(b))
-    with np.errstate(invalid="ignore"):
-        bad = ~((np.abs(a - b) <= rtol * scale) | (np.isnan(a) & np.isnan(b)) | (a == b))
-    return not bad.any(), (np.nanmax(np.abs(a - b) / scale) if a.size else 0.0)
+    if scale is None:
+        with np.errstate(invalid="ignore"):
+            fin = np.where(np.isfinite(b), np.abs(b), 0.0)
+        if b.ndim >= 2:
+            ax = axis % b.ndim
+            scale = fin.max(axis=tuple(i for i in range(b.ndim) if i != ax), keepdims=True)
+            scale = np.maximum(scale, 1e-6 * fin.max()) if fin.size else scale
+        else:
+            scale = fin.max() if fin.size else 1.0
+    scale = np.maximum(np.asarray(scale, dtype=np.float64), 1e-300)
+    with np.errstate(invalid="ignore", over="ignore"):
+        err = np.abs(a - b) / scale
+        same = (np.isnan(a) & np.isnan(b)) | (a == b)
+        bad = ~((err <= rtol) | same)
+        worst = np.nanmax(np.where(same, 0.0, err)) if a.size else 0.0
+    return not bad.any(), float(worst)
+
+
+def close_diag(a, b, rtol=1e-9):
+    """Floating-point diagnostics columns (orbit lengths, log-weights, energy spreads, index statistics): differences
+    of O(H) quantities, compared on the scale max(1, |b|) element by element."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return close(a, b, rtol, scale=np.maximum(1.0, np.where(np.isfinite(b), np.abs(b), 1.0)))
 
 
 def oracle_target(name, d, data=None):

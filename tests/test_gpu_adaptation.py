@@ -33,7 +33,7 @@ def test_default_adaptation_matches_oracle(cuda_lib, target, integrator):
     lp = ot.std_normal if target == "std_normal" else ot.corr_gauss
     q0 = 0.5 * np.random.default_rng(2).standard_normal((4, d))
     s, dg, so, do = run_pair(target, lp, q0, integrator, numIter=120, warmupIter=80, M=8)
-    ok, err = close(s, so)
+    ok, err = close(s, so, axis=-2)
     assert ok, f"draws: {err:.3e}"
     ok, err = close(dg[..., [15, 18]], do[..., [15, 18]], rtol=1e-9)       # adapted H and delta, every iteration
     assert ok, f"adapted H / delta: {err:.3e}"
@@ -46,7 +46,7 @@ def test_adapt_delta_only_and_h_only(cuda_lib):
     q0 = 0.5 * np.random.default_rng(3).standard_normal((3, 5))
     for kw in (dict(adaptH=False, adaptDelta=True), dict(adaptH=True, adaptDelta=False)):
         s, dg, so, do = run_pair("std_normal", ot.std_normal, q0, "R2P", numIter=70, warmupIter=50, M=7, **kw)
-        ok, err = close(s, so)
+        ok, err = close(s, so, axis=-2)
         assert ok, (kw, err)
         ok, err = close(dg[..., [15, 18]], do[..., [15, 18]], rtol=1e-9)
         assert ok, (kw, err)
@@ -80,6 +80,6 @@ def test_record_orbit_stats(cuda_lib, integrator):
         so, do, lo_o, hi_o = wo.WALNUTS(ot.std_normal, q0[c], integrator=KIND[integrator], numIter=60, warmupIter=20,
                                         M=7, seed=5, chain=c, adaptH=True, adaptDelta=True, recordOrbitStats=True)
         for a, b in ((s[c], so), (lo[c], lo_o), (hi[c], hi_o)):
-            ok, err = close(a, b)
+            ok, err = close(a, b, axis=-2)
             assert ok, err
     assert (lo <= s[:, :, 1:]).all() and (s[:, :, 1:] <= hi).all()

@@ -76,7 +76,7 @@ def test_aux_parameters_reach_the_kernel(cuda_lib):
             with np.errstate(all="ignore"):
                 so, do = wo.WALNUTS(ot.std_normal, q0[c], integrator=kind, H0=0.8, delta0=0.2, numIter=30, M=6,
                                     igrAux=wo.AuxPar(**kw), seed=9, chain=c)
-            ok, err = close(s[c], so)
+            ok, err = close(s[c], so, axis=-2)
             assert ok, err
             assert np.array_equal(d[c][:, [1, 6, 7, 8, 9, 19]], do[:, [1, 6, 7, 8, 9, 19]])
 
@@ -95,7 +95,7 @@ def test_default_adaptation(cuda_lib, integrator):
         with np.errstate(all="ignore"):
             so, do = wo.WALNUTS(ot.std_normal, q0[c], integrator=ig[integrator][1], numIter=80, warmupIter=50, M=7,
                                 seed=3, chain=c, adaptH=True, adaptDelta=True)
-        ok, err = close(s[c], so, rtol=1e-8)
+        ok, err = close(s[c], so, rtol=1e-8, axis=-2)
         assert ok, err
         ok, err = close(d[c][:, [15, 18]], do[:, [15, 18]], rtol=1e-8)
         assert ok, err

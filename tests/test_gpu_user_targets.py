@@ -70,7 +70,7 @@ def test_user_target_free_running_with_default_adaptation(cuda_lib):
         with np.errstate(all="ignore"):
             so, do = wo.WALNUTS(ot.smile, q0[c], integrator=wo.ADAPT_R2P, numIter=120, warmupIter=80, M=8, seed=5,
                                 chain=c, adaptH=True, adaptDelta=True)
-        ok, err = close(s[c], so, rtol=1e-8)
+        ok, err = close(s[c], so, rtol=1e-8, axis=-2)
         assert ok, err
         assert np.array_equal(d[c][:, [1, 6, 7, 19]], do[:, [1, 6, 7, 19]])
         ok, err = close(d[c][:, [15, 18]], do[:, [15, 18]], rtol=1e-8)
@@ -95,7 +95,7 @@ def test_user_target_with_data_matches_builtin(cuda_lib):
               adaptDelta=False, seed=11)
     s1, d1 = wb.WALNUTS(tg, q0, **kw)
     s2, d2 = wb.WALNUTS(wb.targets.diag_gauss(sigma), q0, **kw)
-    ok, err = close(s1, s2)
+    ok, err = close(s1, s2, axis=-2)
     assert ok, err
     assert np.array_equal(d1[..., EXACT], d2[..., EXACT])
 
@@ -117,7 +117,7 @@ def test_user_target_d40_spilled_state(cuda_lib):
               adaptDelta=False, seed=12)
     s1, d1 = wb.WALNUTS(tg, q0, **kw)
     s2, d2 = wb.WALNUTS(wb.targets.diag_gauss(sigma), q0, **kw)
-    ok, err = close(s1, s2)
+    ok, err = close(s1, s2, axis=-2)
     assert ok, err
     assert np.array_equal(d1[..., EXACT], d2[..., EXACT])
 

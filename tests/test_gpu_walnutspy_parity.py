@@ -6,7 +6,7 @@ fingerprints (diagnostics columns) exactly.  All calls go through the C-ABI (Cha
 import numpy as np
 import pytest
 
-from tests.helpers import close, oracle_walnutspy
+from tests.helpers import close, close_diag, oracle_walnutspy
 
 pytestmark = pytest.mark.gpu
 
@@ -30,16 +30,19 @@ def check(name, q0, integrator, H0, delta, M, n_iter, seed=1234, chains=None, mi
     out, state = run_cuda(name, q0, integrator, H0, delta, M, n_iter, seed, minC, maxC, data)
     chains = list(range(q0.shape[0])) if chains is None else chains
     draws_o, diag_o = oracle_walnutspy(name, q0, integrator, H0, delta, M, n_iter, seed, chains, minC, maxC, data)
-    ok, err = close(out["draws"][:, chains, :], draws_o)
+    # diagonal Gaussians: every coordinate against ITS standard deviation (north_star: 1e-10 relative)
+    scale = (1.0 / np.sqrt(np.asarray(data["inv_var"]))) if name == "diag_gauss" else None
+    ok, err = close(out["draws"][:, chains, :], draws_o, scale=scale)
+    print(f"{name} d={q0.shape[1]} {integrator} x {n_iter} transitions: worst relative error of the draws {err:.2e}")
     assert ok, f"draws differ: max rel err {err:.3e}"
     dg = out["diag"][:, chains, :]
     assert np.array_equal(dg[..., EXACT_COLS], diag_o[..., EXACT_COLS]), \
         f"control-flow fingerprint differs in cols {[c for c in EXACT_COLS if not np.array_equal(dg[..., c], diag_o[..., c])]}"
-    ok, err = close(dg[..., FLOAT_COLS], diag_o[..., FLOAT_COLS], rtol=float_rtol)
+    ok, err = close_diag(dg[..., FLOAT_COLS], diag_o[..., FLOAT_COLS], rtol=float_rtol)
     assert ok, f"float diagnostics differ: {err:.3e}"
     assert np.array_equal(out["nevalF"][chains], diag_o[..., 6].sum(axis=0).astype(np.uint64))
     assert np.array_equal(out["nevalB"][chains], diag_o[..., 7].sum(axis=0).astype(np.uint64))
-    ok, _ = close(state[chains], draws_o[-1])
+    ok, _ = close(state[chains], draws_o[-1], scale=scale)
     assert ok
     return diag_o
 
@@ -72,7 +75,8 @@ def free_running_horizon(name, q0, integrator, H0, delta, M, n_iter, seed=1234, 
     out, _ = run_cuda(name, q0, integrator, H0, delta, M, n_iter, seed, minC, maxC, data)
     chains = list(range(q0.shape[0]))
     draws_o, _ = oracle_walnutspy(name, q0, integrator, H0, delta, M, n_iter, seed, chains, minC, maxC, data)
-    err = np.max(np.abs(out["draws"] - draws_o) / np.maximum(1.0, np.abs(draws_o)), axis=(1, 2))
+    scale = np.abs(draws_o).max(axis=(0, 1), keepdims=True)        # per-coordinate magnitude, as helpers.close
+    err = np.max(np.abs(out["draws"] - draws_o) / scale, axis=(1, 2))
     bad = np.nonzero(err > 1e-10)[0]
     return (int(bad[0]) if len(bad) else n_iter), err
 
@@ -195,10 +199,10 @@ def test_walnutspy_golden_from_real_reference(cuda_lib, path):
     if m["target"] != "funnel":
         s, d = wb.WALNUTS(tg, z["q0"], numIter=m["n_iter"], **kw)
         assert s.shape == ref_s.shape and d.shape == ref_d.shape
-        ok, err = close(s, ref_s)
+        ok, err = close(s, ref_s, axis=-2)
         assert ok, f"max rel err {err:.3e}"
         assert np.array_equal(d[:, EXACT_COLS], ref_d[:, EXACT_COLS])
-        ok, err = close(d[:, FLOAT_COLS], ref_d[:, FLOAT_COLS], rtol=1e-9)
+        ok, err = close_diag(d[:, FLOAT_COLS], ref_d[:, FLOAT_COLS], rtol=1e-9)
         assert ok, err
     else:
         from walnuts_b200 import ChainBatch
@@ -300,7 +304,8 @@ def test_c2_100_transitions_vs_c_oracle(cuda_lib, integrator):
     out, _ = run_cuda("diag_gauss", q0, integrator, H0, 0.3, 10, n_iter, 4242, data={"inv_var": inv_var})
     for c in (0, 39):
         dr, dg, ne = c_oracle.run_chain("diag_gauss", integrator, q0[c], H0, 0.3, 10, n_iter, 4242, c, inv_var=inv_var)
-        ok, err = close(out["draws"][:, c, :], dr)
+        ok, err = close(out["draws"][:, c, :], dr, scale=sigma)      # relative to each coordinate's sigma_i
+        print(f"C2 shape, {integrator}, chain {c}: worst |dq_i| / sigma_i over {n_iter} free-running transitions {err:.2e}")
         assert ok, f"chain {c}: max rel err {err:.3e}"
         assert np.array_equal(out["diag"][:, c][:, EXACT_COLS], dg[:, EXACT_COLS])
         assert int(out["nevalF"][c] + out["nevalB"][c]) == ne
@@ -367,7 +372,7 @@ def test_yoshida_with_default_adaptation(cuda_lib):
         # The 4th-order integrator's energy errors are ~1e-7 of H, i.e. they carry a RELATIVE rounding error of
         # ~1e-9, and the adaptation feeds them back into delta and H (WALNUTS.py:704-712): agreement of the
         # adapted run is limited to ~1e-8 for ANY two implementations (fixed-(H, delta) parity is 1e-10 above).
-        ok, err = close(s[c], so, rtol=1e-6)
+        ok, err = close(s[c], so, rtol=1e-6, axis=-2)
         assert ok, err
         ok, err = close(d[c][:, [15, 18]], do[:, [15, 18]], rtol=1e-6)
         assert ok, err
@@ -395,7 +400,7 @@ def test_randomised_configurations(cuda_lib, case):
     out, state = run_cuda("diag_gauss", q0, integ, H0, delta, M, n_iter, seed, minC, maxC, {"inv_var": inv_var})
     for c in (0, n_chains - 1):
         dr, dg, ne = c_oracle.run_chain("diag_gauss", integ, q0[c], H0, delta, M, n_iter, seed, c, minC, maxC, inv_var=inv_var)
-        ok, err = close(out["draws"][:, c], dr)
+        ok, err = close(out["draws"][:, c], dr, scale=sigma)
         assert ok, f"d={d} {integ}: max rel err {err:.3e}"
         assert np.array_equal(out["diag"][:, c][:, EXACT_COLS], dg[:, EXACT_COLS]), f"d={d} {integ}"
         assert int(out["nevalF"][c] + out["nevalB"][c]) == ne

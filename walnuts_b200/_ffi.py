@@ -13,14 +13,14 @@ ERRORS = {-1: "WN_EINVAL", -2: "WN_ECUDA", -3: "WN_ENOMEM", -4: "WN_EUNSUPPORTED
 
 # every symbol include/walnuts_cuda.h declares
 SYMBOLS = ["wn_abi_version", "wn_target_id", "wn_register_user_target", "wn_create", "wn_destroy", "wn_set_data", "wn_set_aux", "wn_set_adapt", "wn_set_state",
-           "wn_get_state", "wn_run", "wn_run_stats", "wn_run_async", "wn_sync", "wn_last_kernel_ms", "wn_last_launches",
+           "wn_get_state", "wn_run", "wn_run_stats", "wn_run_async", "wn_sync", "wn_run_host_async", "wn_alloc_pinned", "wn_free_pinned", "wn_last_kernel_ms", "wn_last_launches",
            "wn_last_grad_evals", "wn_moments", "wn_stream", "wn_last_error", "wn_fp64_peak"]
 
 
 class WnConfig(C.Structure):
     _fields_ = [("target", C.c_int32), ("mode", C.c_int32), ("integrator", C.c_int32), ("d", C.c_int32),
                 ("n_chains", C.c_int32), ("device", C.c_int32), ("dg", C.c_int32), ("M", C.c_int32),
-                ("minC", C.c_int32), ("maxC", C.c_int32), ("compat", C.c_int32), ("reserved0", C.c_int32),
+                ("minC", C.c_int32), ("maxC", C.c_int32), ("compat", C.c_int32), ("first_iteration", C.c_int32),
                 ("H0", C.c_double), ("jitter", C.c_double), ("delta", C.c_double),
                 ("r2p_prob0", C.c_double), ("log_p0", C.c_double), ("log_1mp0", C.c_double),
                 ("seed", C.c_uint64), ("chain_offset", C.c_uint64)]
@@ -64,6 +64,9 @@ def load():
     lib.wn_run_stats.argtypes = [vp, C.c_int64, dp, dp, u64p, u64p, dp, dp, C.c_int]
     lib.wn_run_async.argtypes = [vp, C.c_int64, dp, dp, u64p, u64p]
     lib.wn_sync.argtypes = [vp]
+    lib.wn_run_host_async.argtypes = [vp, C.c_int64, dp, dp, dp, u64p, u64p, dp]
+    lib.wn_alloc_pinned.argtypes = [C.c_int64, P(vp)]
+    lib.wn_free_pinned.argtypes = [vp]
     lib.wn_last_kernel_ms.argtypes = [vp, P(C.c_float)]
     lib.wn_last_launches.argtypes = [vp, P(C.c_int64)]
     lib.wn_last_grad_evals.argtypes = [vp, P(C.c_uint64), P(C.c_uint64)]

@@ -30,7 +30,10 @@ def WALNUTS(lpFun, q0, generated=None, integrator=_ig.fixedLeapFrog, H0=0.2, ste
     (numIter, 24) exactly as WALNUTS.py:163,180,724-727; with q0 of shape (n_chains, d) a leading
     chains axis is added.
 
-    `compat=True` (default) reproduces the reference bit-for-bit, including its defect A14(i): the second leaf
+    `compat=True` (default) reproduces the reference's semantics including its defects: every discrete decision
+    (the integer diagnostics columns) is identical and draws agree to 1e-10 relative with the reference fed the same
+    Philox streams (the kernels use FMA contraction, merged kicks and CUDA's libm, so draws are not bit-identical).
+    Defect A14(i): the second leaf
     of a BACKWARD pair never adds its log-weight to the running sum (WALNUTS.py:420 has no counterpart after
     :443-459), which measurably biases adaptive runs on the funnel.  `compat=False` adds it.
     """
@@ -98,7 +101,7 @@ def WALNUTS(lpFun, q0, generated=None, integrator=_ig.fixedLeapFrog, H0=0.2, ste
 
 
 def _pkg_batch(rng, theta, logp, grad, inv_mass, macro_step, max_nuts_depth, max_error, seed, device,
-               compat, chain_offset):
+               compat, chain_offset, first_iteration=1):
     theta = np.array(theta, dtype=np.float64)
     inv_mass = np.array(inv_mass, dtype=np.float64)
     single = theta.ndim == 1
@@ -125,7 +128,7 @@ def _pkg_batch(rng, theta, logp, grad, inv_mass, macro_step, max_nuts_depth, max
     data["inv_mass"] = inv_mass
     cb = ChainBatch(name, th.shape[1], th.shape[0], mode="package", H0=macro_step, delta=max_error,
                     M=max_nuts_depth, seed=seed, chain_offset=chain_offset, device=device, compat=compat,
-                    data=data)
+                    data=data, first_iteration=first_iteration)
     cb.set_state(th)
     return cb, single
 
@@ -145,10 +148,20 @@ def walnuts(rng, theta_init, logp, grad, inv_mass, macro_step, max_nuts_depth, m
 
 
 def walnuts_step(rng, theta, logp, grad, inv_mass, macro_step, max_nuts_depth, max_error, *, seed=None,
-                 device=0, compat=True, chain_offset=0):
-    """walnuts.py:279-359: one transition; returns the next state vector(s)."""
+                 iteration=None, device=0, compat=True, chain_offset=0):
+    """walnuts.py:279-359: one transition; returns the next state vector(s).
+
+    Randomness: the Philox streams are keyed by (seed, chain, iteration).  With `seed=None` a fresh seed is drawn
+    from `rng` on every call, as the reference consumes `rng`.  With a FIXED `seed` the caller must tell the
+    transitions apart: pass `iteration` (1, 2, 3, ... as walnuts() counts them; same seed + same iteration replays
+    the same momentum, directions and uniforms); if it is omitted, one value is drawn from `rng` per call and used
+    as the iteration number, so a loop over walnuts_step(rng, ..., seed=k) never repeats its streams."""
+    if iteration is None:
+        iteration = 1 if seed is None else (int(rng.integers(1, 2 ** 31)) if hasattr(rng, "integers") else 1)
+    if not 1 <= int(iteration) < 2 ** 31:
+        raise ValueError("iteration must be in [1, 2^31)")
     cb, single = _pkg_batch(rng, theta, logp, grad, inv_mass, macro_step, max_nuts_depth, max_error,
-                            seed, device, compat, chain_offset)
+                            seed, device, compat, chain_offset, int(iteration))
     with cb:
         cb.run(1, draws=False, nevals=False)
         out = cb.get_state()

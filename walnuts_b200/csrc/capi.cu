@@ -6,6 +6,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -40,11 +42,15 @@ struct wn_handle {
   int64_t n_p0 = 0, n_p1 = 0;
   double tau = 1.0;
   double inv_var_max = 1.0;
-  uint32_t iter_done = 0;
+  uint32_t iter_done = 0, iter_base = 0;   // iter_base: iter_done at creation (cfg.first_iteration - 1)
   float last_ms = 0.f;
   int64_t last_launches = 0;
   unsigned long long last_tot[2] = {0, 0};
   int num_sms = 148;
+  // grow-only device staging of the host-buffer paths (wn_run / wn_run_stats / wn_run_host_async)
+  double *o_draws = nullptr, *o_diag = nullptr, *o_lo = nullptr, *o_hi = nullptr;
+  uint64_t *o_f = nullptr, *o_b = nullptr;
+  size_t cap_draws = 0, cap_diag = 0, cap_lo = 0, cap_hi = 0;
   std::string err;
 };
 
@@ -70,11 +76,18 @@ struct UserTarget {
   int (*occupancy)(int, int);
   int (*launch)(int, int, const void*, unsigned, void*);
 };
-static std::vector<UserTarget>& user_targets() {
-  static std::vector<UserTarget> v;
+// append-only registry: a deque keeps the addresses of earlier entries stable while wn_register_user_target
+// appends from another host thread; the mutex orders appends against look-ups
+static std::mutex& user_mutex() {
+  static std::mutex m;
+  return m;
+}
+static std::deque<UserTarget>& user_targets() {
+  static std::deque<UserTarget> v;
   return v;
 }
 static const UserTarget* user_target(int id) {
+  std::lock_guard<std::mutex> lock(user_mutex());
   const int i = id - WN_TARGET_USER_BASE;
   return (i >= 0 && i < (int)user_targets().size()) ? &user_targets()[i] : nullptr;
 }
@@ -161,6 +174,7 @@ int wn_register_user_target(const char* path) {
     return WN_EUNSUPPORTED;
   }
   u.d = dim();
+  std::lock_guard<std::mutex> lock(user_mutex());
   user_targets().push_back(u);
   return WN_TARGET_USER_BASE + (int)user_targets().size() - 1;
 }
@@ -198,6 +212,9 @@ int wn_create(const wn_config* cfg, wn_handle** out) {
     if (!(c.jitter >= 0 && c.jitter < 1)) return fail(h, WN_EINVAL, "stepSizeRandScale must be in [0,1)");
   }
   if (c.dg < 0 || c.dg > c.d) return fail(h, WN_EINVAL, "dg must be in [0, d]");
+  if (c.first_iteration < 0) return fail(h, WN_EINVAL, "first_iteration must be >= 0");
+  h->iter_done = c.first_iteration > 1 ? (uint32_t)c.first_iteration - 1u : 0u;
+  h->iter_base = h->iter_done;
   LaunchPlan p;
   if (!pick_plan(c, false, p)) return fail(h, WN_EUNSUPPORTED, "no CUDA kernel for this target/dimension");
   CUDA_TRY(h, cudaSetDevice(c.device));
@@ -220,6 +237,7 @@ void wn_destroy(wn_handle* h) {
     cudaStreamSynchronize(h->stream);
   }
   cudaFree(h->d_state); cudaFree(h->d_scratch); cudaFree(h->d_queue); cudaFree(h->d_totals);
+  cudaFree(h->o_draws); cudaFree(h->o_diag); cudaFree(h->o_lo); cudaFree(h->o_hi); cudaFree(h->o_f); cudaFree(h->o_b);
   cudaFree(h->d_p0); cudaFree(h->d_p1); cudaFree(h->d_p2); cudaFree(h->d_inv_mass); cudaFree(h->d_H); cudaFree(h->d_delta); cudaFree(h->d_adapt_state); cudaFree(h->d_adapt_hist);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -314,7 +332,9 @@ int wn_set_adapt(wn_handle* h, int64_t warmup_iter, int adaptH, double adaptHtar
   if (adaptH && (adaptHtarget < 0.0 || adaptHtarget > 1.0)) return fail(h, WN_EINVAL, "bad adaptHtarget");        // WALNUTS.py:140
   if (adaptDelta && adaptDeltaTarget < 0.0) return fail(h, WN_EINVAL, "bad adaptDeltaTarget");                    // WALNUTS.py:146
   if (adaptDelta && !(adaptDeltaQuantile >= 0.0 && adaptDeltaQuantile <= 1.0)) return fail(h, WN_EINVAL, "bad adaptDeltaQuantile");
-  if (h->iter_done != 0) return fail(h, WN_ESTATE, "wn_set_adapt must precede the first wn_run");
+  if (h->iter_done != h->iter_base) return fail(h, WN_ESTATE, "wn_set_adapt must precede the first wn_run");
+  if (h->iter_base != 0 && warmup_iter > 0 && (adaptH || adaptDelta))
+    return fail(h, WN_EINVAL, "warm-up adaptation needs first_iteration = 1 (the warm-up window is counted in iterations)");
   CUDA_TRY(h, cudaSetDevice(c.device));
   cudaFree(h->d_adapt_state); cudaFree(h->d_adapt_hist);
   h->d_adapt_state = h->d_adapt_hist = nullptr;
@@ -497,54 +517,74 @@ int wn_run(wn_handle* h, int64_t n_iter, double* draws, double* diag, uint64_t* 
   return wn_run_stats(h, n_iter, draws, diag, nevalF, nevalB, nullptr, nullptr, on_device);
 }
 
-int wn_run_stats(wn_handle* h, int64_t n_iter, double* draws, double* diag, uint64_t* nevalF, uint64_t* nevalB,
-                 double* orbit_min, double* orbit_max, int on_device) {
+// device staging of one output of the host-buffer paths: grow-only, owned by the handle
+static int stage(wn_handle* h, double** buf, size_t* cap, size_t n) {
+  if (n <= *cap) return WN_OK;
+  if (*buf) { cudaFree(*buf); *buf = nullptr; *cap = 0; }
+  CUDA_TRY(h, cudaMalloc(buf, n * sizeof(double)));
+  *cap = n;
+  return WN_OK;
+}
+
+static int host_async_impl(wn_handle* h, int64_t n_iter, const double* q_in, double* draws, double* diag,
+                           uint64_t* nevalF, uint64_t* nevalB, double* orbit_min, double* orbit_max, double* q_out) {
   if (!h) return WN_EINVAL;
   if ((orbit_min == nullptr) != (orbit_max == nullptr)) return fail(h, WN_EINVAL, "orbit_min and orbit_max go together");
-  if (on_device) {
-    int rc = run_async_impl(h, n_iter, draws, diag, nevalF, nevalB, orbit_min, orbit_max);
-    if (rc) return rc;
-    return wn_sync(h);
-  }
   if (n_iter <= 0 || n_iter > 0x7fffffff) return fail(h, WN_EINVAL, "n_iter must be positive");
   const wn_config& c = h->cfg;
   CUDA_TRY(h, cudaSetDevice(c.device));
   const size_t nd = draws ? (size_t)n_iter * c.n_chains * c.dg : 0;
   const size_t ng = diag ? (size_t)n_iter * c.n_chains * WN_DIAG_COLS : 0;
-  double *dd = nullptr, *dgp = nullptr, *dlo = nullptr, *dhi = nullptr;
-  uint64_t *df = nullptr, *db = nullptr;
-  int rc = WN_OK;
   const size_t no = orbit_min ? (size_t)n_iter * c.n_chains * c.dg : 0;
-  auto cleanup = [&]() { cudaFree(dd); cudaFree(dgp); cudaFree(df); cudaFree(db); cudaFree(dlo); cudaFree(dhi); };
-#define TRY_OR_CLEAN(expr)                                                              \
-  do {                                                                                  \
-    cudaError_t _e = (expr);                                                            \
-    if (_e != cudaSuccess) {                                                            \
-      cleanup();                                                                        \
-      return fail(h, WN_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));     \
-    }                                                                                   \
-  } while (0)
-  if (nd) TRY_OR_CLEAN(cudaMalloc(&dd, nd * sizeof(double)));
-  if (no) { TRY_OR_CLEAN(cudaMalloc(&dlo, no * sizeof(double))); TRY_OR_CLEAN(cudaMalloc(&dhi, no * sizeof(double))); }
-  if (ng) TRY_OR_CLEAN(cudaMalloc(&dgp, ng * sizeof(double)));
-  if (nevalF) TRY_OR_CLEAN(cudaMalloc(&df, (size_t)c.n_chains * sizeof(uint64_t)));
-  if (nevalB) TRY_OR_CLEAN(cudaMalloc(&db, (size_t)c.n_chains * sizeof(uint64_t)));
-  if (db) TRY_OR_CLEAN(cudaMemsetAsync(db, 0, (size_t)c.n_chains * sizeof(uint64_t), h->stream));
-  rc = run_async_impl(h, n_iter, dd, dgp, df, db, dlo, dhi);
-  if (rc == WN_OK) rc = wn_sync(h);
-  if (rc != WN_OK) { cleanup(); return rc; }
-  if (nd) TRY_OR_CLEAN(cudaMemcpy(draws, dd, nd * sizeof(double), cudaMemcpyDeviceToHost));
-  if (no) {
-    TRY_OR_CLEAN(cudaMemcpy(orbit_min, dlo, no * sizeof(double), cudaMemcpyDeviceToHost));
-    TRY_OR_CLEAN(cudaMemcpy(orbit_max, dhi, no * sizeof(double), cudaMemcpyDeviceToHost));
+  const size_t nc = (size_t)c.n_chains;
+  int rc;
+  if ((rc = stage(h, &h->o_draws, &h->cap_draws, nd))) return rc;
+  if ((rc = stage(h, &h->o_diag, &h->cap_diag, ng))) return rc;
+  if ((rc = stage(h, &h->o_lo, &h->cap_lo, no))) return rc;
+  if ((rc = stage(h, &h->o_hi, &h->cap_hi, no))) return rc;
+  if (nevalF && !h->o_f) CUDA_TRY(h, cudaMalloc(&h->o_f, nc * sizeof(uint64_t)));
+  if (nevalB && !h->o_b) CUDA_TRY(h, cudaMalloc(&h->o_b, nc * sizeof(uint64_t)));
+  if (q_in) {
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_state, q_in, nc * c.d * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    h->have_state = true;
   }
-  if (ng) TRY_OR_CLEAN(cudaMemcpy(diag, dgp, ng * sizeof(double), cudaMemcpyDeviceToHost));
-  if (nevalF) TRY_OR_CLEAN(cudaMemcpy(nevalF, df, (size_t)c.n_chains * sizeof(uint64_t), cudaMemcpyDeviceToHost));
-  if (nevalB) TRY_OR_CLEAN(cudaMemcpy(nevalB, db, (size_t)c.n_chains * sizeof(uint64_t), cudaMemcpyDeviceToHost));
-  cleanup();
-#undef TRY_OR_CLEAN
+  if (nevalB) CUDA_TRY(h, cudaMemsetAsync(h->o_b, 0, nc * sizeof(uint64_t), h->stream));   // package mode leaves it untouched
+  rc = run_async_impl(h, n_iter, nd ? h->o_draws : nullptr, ng ? h->o_diag : nullptr, nevalF ? h->o_f : nullptr,
+                      nevalB ? h->o_b : nullptr, no ? h->o_lo : nullptr, no ? h->o_hi : nullptr);
+  if (rc) return rc;
+  if (nd) CUDA_TRY(h, cudaMemcpyAsync(draws, h->o_draws, nd * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (no) {
+    CUDA_TRY(h, cudaMemcpyAsync(orbit_min, h->o_lo, no * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(orbit_max, h->o_hi, no * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  }
+  if (ng) CUDA_TRY(h, cudaMemcpyAsync(diag, h->o_diag, ng * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (nevalF) CUDA_TRY(h, cudaMemcpyAsync(nevalF, h->o_f, nc * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
+  if (nevalB) CUDA_TRY(h, cudaMemcpyAsync(nevalB, h->o_b, nc * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
+  if (q_out) CUDA_TRY(h, cudaMemcpyAsync(q_out, h->d_state, nc * c.d * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   return WN_OK;
 }
+
+int wn_run_host_async(wn_handle* h, int64_t n_iter, const double* q_in, double* draws, double* diag,
+                      uint64_t* nevalF, uint64_t* nevalB, double* q_out) {
+  return host_async_impl(h, n_iter, q_in, draws, diag, nevalF, nevalB, nullptr, nullptr, q_out);
+}
+
+int wn_run_stats(wn_handle* h, int64_t n_iter, double* draws, double* diag, uint64_t* nevalF, uint64_t* nevalB,
+                 double* orbit_min, double* orbit_max, int on_device) {
+  if (!h) return WN_EINVAL;
+  if ((orbit_min == nullptr) != (orbit_max == nullptr)) return fail(h, WN_EINVAL, "orbit_min and orbit_max go together");
+  int rc = on_device ? run_async_impl(h, n_iter, draws, diag, nevalF, nevalB, orbit_min, orbit_max)
+                     : host_async_impl(h, n_iter, nullptr, draws, diag, nevalF, nevalB, orbit_min, orbit_max, nullptr);
+  if (rc) return rc;
+  return wn_sync(h);
+}
+
+int wn_alloc_pinned(int64_t bytes, void** out) {
+  if (!out || bytes <= 0) return WN_EINVAL;
+  *out = nullptr;
+  return cudaHostAlloc(out, (size_t)bytes, cudaHostAllocPortable) == cudaSuccess ? WN_OK : WN_ENOMEM;
+}
+int wn_free_pinned(void* p) { return (!p || cudaFreeHost(p) == cudaSuccess) ? WN_OK : WN_ECUDA; }
 
 int wn_last_kernel_ms(wn_handle* h, float* ms) {
   if (!h || !ms) return WN_EINVAL;

@@ -2,9 +2,12 @@
 
 numpy arrays are the default I/O; torch CUDA tensors are accepted as optional device-resident I/O
 (their data pointers are passed straight through; torch is not imported unless one is given).
+Every buffer handed to the library is checked for dtype, contiguity and exact size first: the C-ABI takes raw
+pointers and trusts them.
 """
 import ctypes as C
 import math
+import weakref
 
 import numpy as np
 
@@ -17,14 +20,46 @@ def _is_torch(x):
     return type(x).__module__.startswith("torch")
 
 
-def _ptr(x):
+def _ptr(x, numel=None, kind="f8", what="buffer"):
+    """(pointer, on_device) of a float64 / uint64 buffer after checking dtype, contiguity and element count."""
     if x is None:
         return None, 0
     if _is_torch(x):
         if not x.is_cuda or not x.is_contiguous():
-            raise WalnutsError("torch tensors passed to walnuts_b200 must be contiguous CUDA tensors")
+            raise WalnutsError(f"{what}: torch tensors passed to walnuts_b200 must be contiguous CUDA tensors")
+        name = str(x.dtype)
+        ok = name == "torch.float64" if kind == "f8" else name in ("torch.uint64", "torch.int64")
+        if not ok:
+            raise WalnutsError(f"{what}: expected {'float64' if kind == 'f8' else 'uint64/int64'}, got {name}")
+        if numel is not None and x.numel() != numel:
+            raise WalnutsError(f"{what}: expected {numel} elements, got {x.numel()}")
         return C.c_void_p(x.data_ptr()), 1
+    if not isinstance(x, np.ndarray):
+        raise WalnutsError(f"{what}: expected a numpy array or a torch CUDA tensor")
+    ok = x.dtype == np.float64 if kind == "f8" else x.dtype in (np.uint64, np.int64)
+    if not ok:
+        raise WalnutsError(f"{what}: expected {'float64' if kind == 'f8' else 'uint64/int64'}, got {x.dtype}")
+    if not x.flags.c_contiguous:
+        raise WalnutsError(f"{what}: numpy buffers must be C-contiguous")
+    if numel is not None and x.size != numel:
+        raise WalnutsError(f"{what}: expected {numel} elements, got {x.size}")
     return C.c_void_p(x.ctypes.data), 0
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """numpy array over page-locked host memory (wn_alloc_pinned): copies through wn_run_host_async are then
+    truly asynchronous.  The memory is released when the array (and every view of it) is gone."""
+    lib = _ffi.load()
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    p = C.c_void_p()
+    rc = lib.wn_alloc_pinned(max(n, 1), C.byref(p))
+    if rc != 0:
+        raise WalnutsError(f"wn_alloc_pinned({n}): {_ffi.ERRORS.get(rc, rc)}")
+    buf = (C.c_char * max(n, 1)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    weakref.finalize(buf, lib.wn_free_pinned, p)
+    return arr
 
 
 class ChainBatch:
@@ -32,7 +67,7 @@ class ChainBatch:
 
     def __init__(self, target, d, n_chains, mode="walnutspy", integrator="fixed", H0=0.2, jitter=0.2,
                  delta=0.05, M=10, minC=0, maxC=10, r2p_prob0=2.0 / 3.0, seed=0, chain_offset=0,
-                 device=0, dg=None, compat=True, data=None):
+                 device=0, dg=None, compat=True, data=None, first_iteration=1):
         self._lib = _ffi.load()
         self._h = C.c_void_p()
         cfg = _ffi.WnConfig()
@@ -43,6 +78,7 @@ class ChainBatch:
         cfg.dg = int(d if dg is None else dg)
         cfg.M, cfg.minC, cfg.maxC = int(M), int(minC), int(maxC)
         cfg.compat = int(bool(compat))
+        cfg.first_iteration = int(first_iteration)
         cfg.H0, cfg.jitter, cfg.delta = float(H0), float(jitter), float(delta)
         cfg.r2p_prob0 = float(r2p_prob0)
         # logs computed by the host libm exactly as the reference does (adaptiveIntegrators.py:433,437)
@@ -92,7 +128,7 @@ class ChainBatch:
             n = arr.size
         else:
             n = arr.numel()
-        p, dev = _ptr(arr)
+        p, dev = _ptr(arr, what=f"set_data({key})")
         self._check(self._lib.wn_set_data(self._h, key.encode(), p, n, dev), f"wn_set_data({key})")
 
     def set_aux(self, maxFPiter=None, FPtol=None, rescaledGradThresh=None):
@@ -111,13 +147,13 @@ class ChainBatch:
     def set_state(self, q):
         if not _is_torch(q):
             q = np.ascontiguousarray(np.broadcast_to(np.asarray(q, dtype=np.float64), (self.n_chains, self.d)))
-        p, dev = _ptr(q)
+        p, dev = _ptr(q, self.n_chains * self.d, what="set_state")
         self._check(self._lib.wn_set_state(self._h, p, dev), "wn_set_state")
 
     def get_state(self, out=None):
         if out is None:
             out = np.empty((self.n_chains, self.d))
-        p, dev = _ptr(out)
+        p, dev = _ptr(out, self.n_chains * self.d, what="get_state(out)")
         self._check(self._lib.wn_get_state(self._h, p, dev), "wn_get_state")
         return out
 
@@ -132,18 +168,42 @@ class ChainBatch:
         b_arr = np.zeros(self.n_chains, dtype=np.uint64) if nevals else None
         lo = np.empty((n_iter, self.n_chains, self.dg)) if orbit_stats else None
         hi = np.empty((n_iter, self.n_chains, self.dg)) if orbit_stats else None
-        rc = self._lib.wn_run_stats(self._h, n_iter, _ptr(d_arr)[0], _ptr(g_arr)[0], _ptr(f_arr)[0], _ptr(b_arr)[0],
-                                    _ptr(lo)[0], _ptr(hi)[0], 0)
+        rc = self._lib.wn_run_stats(self._h, n_iter, _ptr(d_arr)[0], _ptr(g_arr)[0], _ptr(f_arr, kind="u8")[0],
+                                    _ptr(b_arr, kind="u8")[0], _ptr(lo)[0], _ptr(hi)[0], 0)
         self._check(rc, "wn_run")
         out.update(draws=d_arr, diag=g_arr, nevalF=f_arr, nevalB=b_arr, orbit_min=lo, orbit_max=hi)
         return out
 
+    def _out_ptrs(self, n_iter, draws, diag, nevalF, nevalB, want_device):
+        n, k = int(n_iter) * self.n_chains, self.n_chains
+        bufs = ((draws, n * self.dg, "f8", "draws"), (diag, n * _ffi.DIAG_COLS, "f8", "diag"),
+                (nevalF, k, "u8", "nevalF"), (nevalB, k, "u8", "nevalB"))
+        ptrs = []
+        for x, numel, kind, what in bufs:
+            p, dev = _ptr(x, numel, kind, what)
+            if x is not None and dev != want_device:
+                raise WalnutsError(f"{what}: expected a {'torch CUDA tensor' if want_device else 'host numpy array'}")
+            ptrs.append(p)
+        return ptrs
+
     def run_device(self, n_iter, draws=None, diag=None, nevalF=None, nevalB=None, sync=True):
-        """Device-buffer path: torch CUDA tensors (or None) are filled in place."""
-        ptrs = [_ptr(x)[0] for x in (draws, diag, nevalF, nevalB)]
+        """Device-buffer path: torch CUDA tensors (or None) of shapes (n_iter, n_chains, dg), (n_iter, n_chains, 24),
+        (n_chains,), (n_chains,) are filled in place."""
+        ptrs = self._out_ptrs(n_iter, draws, diag, nevalF, nevalB, 1)
         self._check(self._lib.wn_run_async(self._h, int(n_iter), *ptrs), "wn_run_async")
         if sync:
             self.sync()
+
+    def run_host_async(self, n_iter, q_in=None, draws=None, diag=None, nevalF=None, nevalB=None, q_out=None):
+        """The whole step on HOST buffers, enqueued on the handle's stream (wn_run_host_async): positions in,
+        n_iter transitions, draws / diag / nevals / positions out.  Use `pinned_empty` buffers and two handles per
+        device to overlap the copies of one with the kernel of the other; finish with sync()."""
+        ptrs = self._out_ptrs(n_iter, draws, diag, nevalF, nevalB, 0)
+        pin, d0 = _ptr(q_in, self.n_chains * self.d, what="q_in")
+        pout, d1 = _ptr(q_out, self.n_chains * self.d, what="q_out")
+        if d0 or d1:
+            raise WalnutsError("run_host_async takes host buffers")
+        self._check(self._lib.wn_run_host_async(self._h, int(n_iter), pin, *ptrs, pout), "wn_run_host_async")
 
     def sync(self):
         self._check(self._lib.wn_sync(self._h), "wn_sync")
@@ -163,9 +223,14 @@ class ChainBatch:
         self._check(self._lib.wn_last_grad_evals(self._h, C.byref(f), C.byref(b)), "wn_last_grad_evals")
         return int(f.value), int(b.value)
 
-    def moments(self):
-        mean, var = np.empty(self.d), np.empty(self.d)
-        self._check(self._lib.wn_moments(self._h, _ptr(mean)[0], _ptr(var)[0]), "wn_moments")
+    def moments(self, mean=None, var=None):
+        mean = np.empty(self.d) if mean is None else mean
+        var = np.empty(self.d) if var is None else var
+        pm, d0 = _ptr(mean, self.d, what="moments(mean)")
+        pv, d1 = _ptr(var, self.d, what="moments(var)")
+        if d0 or d1:
+            raise WalnutsError("moments() fills host arrays")
+        self._check(self._lib.wn_moments(self._h, pm, pv), "wn_moments")
         return mean, var
 
     @property
