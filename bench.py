@@ -41,11 +41,13 @@ D = 1000
 CHAINS_PER_GPU = 65536
 MONITOR = 16                      # coordinates monitored for ESS (spread over the sigma range)
 
-# Workloads.  flop_per_eval = ALGORITHMIC FP64 work per gradient evaluation (= one leapfrog micro-step incl. the energy)
-# of SURVEY.md section 8(d); C2/R2P additionally reports the 4 flop per coordinate its kernel executes.
+# Workloads.  flop_per_eval = FP64 work per gradient evaluation (= one leapfrog micro-step incl. the energy) of SURVEY.md
+# section 8(d), the roofline numerator -- except for C2 / R2P, whose kernel EXECUTES only 4 flop per coordinate (merged
+# kicks, linear gradient folded into the kick, energies only where they are consumed: DESIGN.md section 6): there the
+# executed work is the numerator (`frac`), and the figure at SURVEY's 12 flop per coordinate is reported next to it.
 WORKLOADS = {
     "c2": dict(target="diag_gauss", d=D, mode="walnutspy", integrator="R2P", H0=0.5, delta=0.3, M=10, minC=0, maxC=10,
-               chains=CHAINS_PER_GPU, iters=1, monitor=MONITOR, flop_per_eval=12.0 * D,
+               chains=CHAINS_PER_GPU, iters=1, monitor=MONITOR, flop_per_eval=4.0 * D, flop_per_eval_survey=12.0 * D,
                workload="diag_gauss_d1000_sigma_logspace(-2,2)_R2P"),
     "c1": dict(target="std_normal", d=100, mode="package", integrator="fixed", H0=2.0, delta=0.1, M=10, minC=0, maxC=10,
                chains=65536, iters=4, monitor=8, flop_per_eval=12.0 * 100, steps_cap=5, warmup_cap=3,
@@ -63,12 +65,16 @@ WORKLOADS = {
                maxC=10, chains=131072, iters=1, monitor=8, flop_per_eval=4.0e4, steps_cap=3, warmup_cap=2,
                workload="stock_watson_T252_R2P_M14_minC3 (mainSW.py:41-49); 131072 chains per GPU"),
     "c2_1m": dict(target="diag_gauss", d=D, mode="walnutspy", integrator="R2P", H0=0.5, delta=0.3, M=10, minC=0,
-                  maxC=10, chains=1048576, iters=1, monitor=MONITOR, flop_per_eval=12.0 * D, steps_cap=1, warmup_cap=0,
+                  maxC=10, chains=1048576, iters=1, monitor=MONITOR, flop_per_eval=4.0 * D,
+                  flop_per_eval_survey=12.0 * D, steps_cap=1, warmup_cap=0,
                   single_gpu_only=True, e2e=False,
                   workload="diag_gauss_d1000_R2P, 1 048 576 concurrent chains on ONE GPU (kernel warm from the headline leg)"),
 }
 CONFIG_ORDER = ["c1", "c2_nuts", "c3", "c4", "c5", "c2_1m"]
-ESS_CHAINS, ESS_DRAWS = 1184, 1024      # 2 chains per resident slot of the d = 1000 kernel (148 SMs x 4 blocks)
+# min-ESS leg: one chain per resident slot of the d = 1000 kernel (148 SMs x 4 blocks) x 2048 draws.  The slowest
+# coordinate (sigma = 100) has an autocorrelation time of ~700 transitions at this tuning, so the chains must be long;
+# the estimator pools 592 x N_GPU chains that start from exact draws of the target.
+ESS_CHAINS, ESS_DRAWS = 592, 2048
 
 
 def sigma_vec():
@@ -220,8 +226,14 @@ _POOL = None
 def _pool(cores):
     global _POOL
     if _POOL is None:
+        import atexit
         import multiprocessing as mp
+        # the reference is single-threaded: one chain per process and ONE BLAS / OpenMP thread per process (the
+        # variables must be in the environment before the children import numpy)
+        for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+            os.environ[var] = "1"
         _POOL = mp.get_context("spawn").Pool(cores)
+        atexit.register(_POOL.terminate)
     return _POOL
 
 
@@ -410,9 +422,14 @@ def gpu_leg(env, name, steps, warmup, chains=None, e2e=True, fp64_peak=None, kee
            "roofline": {"bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
                         "frac": (ach / fp64_peak) if fp64_peak else None, "flop_per_eval": spec["flop_per_eval"],
                         "traffic": None,
-                        "note": "achieved = SURVEY.md 8(d) algorithmic flop per gradient evaluation x evaluations of one "
-                                "launch / its CUDA-event duration; peak = FP64 FMA micro-benchmark of this run "
-                                "(MEASURED_PEAKS.json has no FP64 entry); register-resident chains: not HBM-bound"}}
+                        **({"flop_per_eval_survey": spec["flop_per_eval_survey"],
+                            "achieved_at_survey_flop": ach * spec["flop_per_eval_survey"] / spec["flop_per_eval"],
+                            "frac_at_survey_flop": (ach * spec["flop_per_eval_survey"] / spec["flop_per_eval"] / fp64_peak)
+                            if fp64_peak else None} if "flop_per_eval_survey" in spec else {}),
+                        "note": "achieved = flop_per_eval (SURVEY.md 8(d) algorithmic FP64 work per gradient evaluation; "
+                                "C2/R2P: the 4 flop per coordinate the kernel executes) x evaluations of one launch / its "
+                                "CUDA-event duration; peak = FP64 FMA micro-benchmark of this run (MEASURED_PEAKS.json has "
+                                "no FP64 entry); register-resident chains: not HBM-bound"}}
     if e2e_wall_max > 0:
         out["e2e"] = {"value": e2e_evals_all / e2e_wall_max, "unit": "grad_evals/s", "h2d_bytes_per_step": h2d,
                       "d2h_bytes_per_step": d2h, "handles_per_gpu": len(halves)}
@@ -442,11 +459,12 @@ def ess_leg(env, chains=ESS_CHAINS, n_draws=ESS_DRAWS):
         parts = [torch.empty_like(draws) for _ in range(env.world)]
         env.dist.all_gather(parts, draws)                      # the one collective: monitored draws over NVLink
         draws = torch.cat(parts, 1)
-    per, rh = [], []
+    per, rh, half = [], [], []
     if env.rank == 0:
         for j in range(MONITOR):
             e, r = diagnostics.ess_bulk(draws[:, :, j].t().contiguous())
             per.append(float(e)); rh.append(float(r))
+            half.append(float(diagnostics.ess_bulk(draws[:n_draws // 2, :, j].t().contiguous())[0]))
     sig = sigma_vec()[:MONITOR]
     if env.rank != 0:
         return None
@@ -456,6 +474,7 @@ def ess_leg(env, chains=ESS_CHAINS, n_draws=ESS_DRAWS):
             "grad_evals": evals_all, "min_ess": per[k], "min_ess_per_sec": per[k] / (ms_max * 1e-3),
             "min_ess_per_grad_eval": per[k] / evals_all, "slowest_sigma": float(sig[k]),
             "tau_max_draws": total / per[k], "split_chain_length": n_draws // 2, "rhat_max": float(np.nanmax(rh)),
+            "min_ess_first_half_of_draws": half[k],        # ESS must grow with the draws: ~ half of min_ess
             "ess_per_coordinate": per, "rhat_per_coordinate": rh, "sigma_monitored": [float(x) for x in sig],
             "estimator": "bulk ESS: rank-normalised, split chains, Geyer initial monotone sequence on chain-averaged "
                          "autocorrelations with all lags available (Vehtari et al. 2021 = arviz.ess default, "
@@ -540,12 +559,7 @@ def main():
         hbm_peak = 6650.0
     spec = WORKLOADS["c2"]
     roof = head["roofline"]
-    # C2 / R2P: the kernel EXECUTES 4 flop per coordinate and gradient evaluation (merged kicks, linear gradient folded
-    # into the kick, energies only where they are consumed: DESIGN.md section 6) against the 12 of SURVEY.md 8(d);
-    # `frac` is the executed work over the measured peak, the 12-flop figure is reported next to it
-    roof.update(achieved=roof["achieved"] * 4.0 / 12.0, frac=roof["frac"] * 4.0 / 12.0, flop_per_eval=4.0 * D,
-                achieved_at_12_flop_per_coord=roof["achieved"], frac_at_12_flop_per_coord=roof["frac"],
-                peak_source=peak_src,
+    roof.update(peak_source=peak_src,
                 hbm={"streaming_model_gbs": head["value"] / env.world * 48 * D / 1e9, "peak_gbs": hbm_peak,
                      "note": "SURVEY.md 8(d) streaming model (48 d bytes per evaluation if q, v, g went through HBM every "
                              "micro-step) vs the measured HBM peak: the chains are register-resident, HBM is not the bound"})

@@ -178,6 +178,30 @@ int wn_last_grad_evals(wn_handle* h, uint64_t* forward, uint64_t* backward);
  * (unbiased).  Multi-GPU callers reduce (n, sum, sumsq) themselves. */
 int wn_moments(wn_handle* h, double* mean, double* var);
 
+/* ---- multi-GPU: chains shard across GPUs (cfg.chain_offset) with no exchange while sampling; the collectives below
+ * are the only cross-GPU traffic ("NCCL inside if multi-GPU").  NCCL is bound at run time
+ * (dlopen of libnccl.so.2; a copy already loaded by the process, e.g. torch's, is shared). ----
+ * wn_comm_load: optional explicit path of libnccl.so.2.
+ * Multi-process (one rank per GPU): rank 0 calls wn_comm_unique_id, ships the 128 bytes to the other ranks by any
+ * means, every rank calls wn_comm_init_rank.  Single process: wn_comm_init_all over one handle per GPU (the later
+ * collective calls must then be issued concurrently, one host thread per handle). */
+int wn_comm_load(const char* libnccl_path);
+int wn_comm_unique_id(void* id128);
+int wn_comm_init_rank(wn_handle* h, int nranks, int rank, const void* id128);
+int wn_comm_init_all(wn_handle** hs, int n);
+int wn_comm_destroy(wn_handle* h);
+
+/* Bulk effective sample size and split-R-hat per monitored coordinate (rank-normalised, split chains, Geyer's
+ * initial monotone sequence over all lags: Vehtari et al. 2021 = arviz.ess, the quantity of the reference's
+ * mainGaussESS.py:50-55) of draws [n_iter, n_chains, dg] as written by wn_run, computed on the device.  With a
+ * communicator the draws of ALL ranks are pooled by one NCCL all-gather (every rank passes the same n_iter,
+ * n_chains, dg and receives the same result).  split = 0 keeps whole chains.  ess, rhat: host arrays [dg]. */
+int wn_ess_rhat(wn_handle* h, const double* draws, int64_t n_iter, int64_t n_chains, int32_t dg, int on_device,
+                int32_t split, double* ess, double* rhat);
+
+/* wn_moments over the chains of ALL ranks of the communicator (two all-reduces of d + 1 doubles). */
+int wn_moments_all(wn_handle* h, double* mean, double* var);
+
 /* the CUDA stream (cudaStream_t) owned by the handle, for event timing by the caller */
 void* wn_stream(wn_handle* h);
 

@@ -66,6 +66,10 @@ def package_cases():
              macro_step=1.3, max_depth=8, max_error=0.2, n_iter=30, seed=7, chain=2),
         dict(name="pkg_funnel4", target="funnel_pkg", theta0=np.array([0.5, .1, .2, -.3]), inv_mass=np.ones(4),
              macro_step=1.0, max_depth=6, max_error=0.3, n_iter=12, seed=8, chain=5),
+        # BASELINE config 1 at its full shape: 100-d standard normal, test/test.py:10-18 settings, depth 10, the
+        # first 100 transitions (north_star parity statement)
+        dict(name="pkg_std100_c1", target="std_normal", theta0=np.zeros(100), inv_mass=np.ones(100), macro_step=2.0,
+             max_depth=10, max_error=0.1, n_iter=100, seed=123, chain=0),
         dict(name="pkg_std3_ell0_defect", target="std_normal", theta0=np.full(3, 0.2), inv_mass=np.ones(3),
              macro_step=0.5, max_depth=5, max_error=0.1, n_iter=12, seed=9, chain=1),
     ]

@@ -83,3 +83,31 @@ def test_record_orbit_stats(cuda_lib, integrator):
             ok, err = close(a, b, axis=-2)
             assert ok, err
     assert (lo <= s[:, :, 1:]).all() and (s[:, :, 1:] <= hi).all()
+
+
+def test_record_orbit_stats_with_index_generator(cuda_lib):
+    """The reference's flagship call: recordOrbitStats=True together with generated=gen, gen(q) = [q[0], q[1]]
+    (WALNUTSpy_examples/funnel/mainFunnel.py:19-20,35-42): orbit minima / maxima of the selected coordinates."""
+    import walnuts_b200 as wb
+
+    def gen(q):
+        return np.array([q[0], q[1]])
+    rng = np.random.default_rng(3)
+    q0 = np.empty((3, 11))
+    q0[:, 0] = rng.standard_normal(3)
+    q0[:, 1:] = np.exp(0.5 * q0[:, :1]) * rng.standard_normal((3, 10))
+    kw = dict(integrator=wb.adaptLeapFrogR2P, M=8, H0=0.3, delta0=0.3, numIter=12, warmupIter=0, seed=6)
+    s, d, lo, hi = wb.WALNUTS(wb.targets.funnel10, q0, generated=gen, recordOrbitStats=True, **kw)
+    s_all, d_all, lo_all, hi_all = wb.WALNUTS(wb.targets.funnel10, q0, recordOrbitStats=True, **kw)
+    assert s.shape == (3, 2, 13) and lo.shape == (3, 2, 12) and hi.shape == (3, 2, 12)
+    assert np.array_equal(s, s_all[:, :2]) and np.array_equal(d, d_all)
+    assert np.array_equal(lo, lo_all[:, :2]) and np.array_equal(hi, hi_all[:, :2])
+    for c in range(3):          # and the oracle (identity statistics, sliced) on the first transitions
+        so, do, lo_o, hi_o = wo.WALNUTS(ot.funnel10, q0[c], integrator=KIND["R2P"], numIter=3, M=8, H0=0.3, delta0=0.3,
+                                        seed=6, chain=c, recordOrbitStats=True)
+        ok, err = close(lo[c][:, :3], lo_o[:2], axis=-2)
+        assert ok, err
+        ok, err = close(hi[c][:, :3], hi_o[:2], axis=-2)
+        assert ok, err
+    with pytest.raises(NotImplementedError):
+        wb.WALNUTS(wb.targets.funnel10, q0, generated=lambda q: np.array([q[0] + q[1]]), recordOrbitStats=True, **kw)

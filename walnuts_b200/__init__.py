@@ -7,7 +7,7 @@ Drop-in call surfaces of the reference (bob-carpenter/walnuts):
 with `lpFun` / `logp` taken from the CUDA target registry in `walnuts_b200.targets`.
 """
 from ._ffi import WalnutsError  # noqa: F401
-from .sampler import ChainBatch, fp64_peak  # noqa: F401
+from .sampler import ChainBatch, fp64_peak, pinned_empty, comm_unique_id, comm_init_all  # noqa: F401
 from . import targets, integrators  # noqa: F401
 from .integrators import (fixedLeapFrog, adaptLeapFrogD, adaptLeapFrogR2P, adaptYoshidaD,  # noqa: F401
                           adaptLeapFrogFlowD, adaptImplicitMidpointD, adaptRescaledLeapFrogD, integratorAuxPar)

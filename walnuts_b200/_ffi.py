@@ -14,7 +14,9 @@ ERRORS = {-1: "WN_EINVAL", -2: "WN_ECUDA", -3: "WN_ENOMEM", -4: "WN_EUNSUPPORTED
 # every symbol include/walnuts_cuda.h declares
 SYMBOLS = ["wn_abi_version", "wn_target_id", "wn_register_user_target", "wn_create", "wn_destroy", "wn_set_data", "wn_set_aux", "wn_set_adapt", "wn_set_state",
            "wn_get_state", "wn_run", "wn_run_stats", "wn_run_async", "wn_sync", "wn_run_host_async", "wn_alloc_pinned", "wn_free_pinned", "wn_last_kernel_ms", "wn_last_launches",
-           "wn_last_grad_evals", "wn_moments", "wn_stream", "wn_last_error", "wn_fp64_peak"]
+           "wn_last_grad_evals", "wn_moments", "wn_stream", "wn_last_error", "wn_fp64_peak",
+           "wn_comm_load", "wn_comm_unique_id", "wn_comm_init_rank", "wn_comm_init_all", "wn_comm_destroy",
+           "wn_ess_rhat", "wn_moments_all"]
 
 
 class WnConfig(C.Structure):
@@ -71,6 +73,13 @@ def load():
     lib.wn_last_launches.argtypes = [vp, P(C.c_int64)]
     lib.wn_last_grad_evals.argtypes = [vp, P(C.c_uint64), P(C.c_uint64)]
     lib.wn_moments.argtypes = [vp, dp, dp]
+    lib.wn_comm_load.argtypes = [C.c_char_p]
+    lib.wn_comm_unique_id.argtypes = [vp]
+    lib.wn_comm_init_rank.argtypes = [vp, C.c_int, C.c_int, vp]
+    lib.wn_comm_init_all.argtypes = [P(vp), C.c_int]
+    lib.wn_comm_destroy.argtypes = [vp]
+    lib.wn_ess_rhat.argtypes = [vp, dp, C.c_int64, C.c_int64, C.c_int32, C.c_int, C.c_int32, dp, dp]
+    lib.wn_moments_all.argtypes = [vp, dp, dp]
     lib.wn_stream.argtypes = [vp]
     lib.wn_stream.restype = vp
     lib.wn_last_error.argtypes = [vp]

@@ -20,10 +20,46 @@ def _seed_from_global():
     return int(np.random.randint(0, 2 ** 62))
 
 
+def _index_generator(generated, d):
+    """If `generated` only SELECTS coordinates (the reference's example scripts: `gen(q) = np.array([q[0], q[1]])`,
+    WALNUTSpy_examples/funnel/mainFunnel.py:19-20), return the selected indices, else None.  Probed with two vectors
+    of distinct values: every output must reproduce one input coordinate exactly, the same one both times."""
+    rng = np.random.default_rng(12345)
+    idx = None
+    for _ in range(2):
+        x = rng.permutation(d).astype(np.float64) + rng.uniform(0.1, 0.9)
+        try:
+            y = np.asarray(generated(x), dtype=np.float64).ravel()
+        except Exception:
+            return None
+        pos = {v: i for i, v in enumerate(x)}
+        cur = [pos.get(v) for v in y]
+        if any(c is None for c in cur) or (idx is not None and cur != idx):
+            return None
+        idx = cur
+    return np.asarray(idx, dtype=int)
+
+
+def _over_devices(fn, x, devices, chain_offset):
+    """Shard the chains axis of `x` (n_chains, d) over `devices` in contiguous blocks and run fn(x_shard, device,
+    chain_offset) for every shard on its own host thread (ctypes releases the GIL inside the library, so the GPUs
+    sample concurrently; no exchange between them: chains are independent, and the Philox streams are keyed by the
+    GLOBAL chain id, so the draws do not depend on the number of devices).  Returns the per-shard results."""
+    from concurrent.futures import ThreadPoolExecutor
+    n = x.shape[0]
+    devices = list(devices)
+    if n < len(devices):
+        devices = devices[:n]
+    bounds = np.linspace(0, n, len(devices) + 1).astype(int)
+    jobs = [(x[bounds[k]:bounds[k + 1]], dev, chain_offset + int(bounds[k])) for k, dev in enumerate(devices)]
+    with ThreadPoolExecutor(max_workers=len(jobs)) as ex:
+        return list(ex.map(lambda j: fn(*j), jobs))
+
+
 def WALNUTS(lpFun, q0, generated=None, integrator=_ig.fixedLeapFrog, H0=0.2, stepSizeRandScale=0.2,
             delta0=0.05, numIter=2000, warmupIter=1000, M=10, igrAux=None, adaptH=True,
             adaptHtarget=0.8, adaptDelta=True, adaptDeltaTarget=0.6, adaptDeltaQuantile=0.9,
-            recordOrbitStats=False, *, seed=None, device=0, chain_offset=0, compat=True):
+            recordOrbitStats=False, *, seed=None, device=0, devices=None, chain_offset=0, compat=True):
     """Many-chain WALNUTS/NUTS with the WALNUTSpy driver semantics (WALNUTS.py:111-129 arguments).
 
     Returns (samples, diagnostics): for a single chain (`q0.ndim == 1`) shapes are (dg, numIter+1) and
@@ -41,9 +77,6 @@ def WALNUTS(lpFun, q0, generated=None, integrator=_ig.fixedLeapFrog, H0=0.2, ste
         raise ValueError("bad adaptHtarget")          # sys.exit in the reference, WALNUTS.py:140
     if adaptDelta and adaptDeltaTarget < 0.0:
         raise ValueError("bad adaptDeltaTarget")      # WALNUTS.py:146
-    if recordOrbitStats and generated is not None:
-        raise NotImplementedError("recordOrbitStats with a custom `generated` is not available on the GPU: the "
-                                  "orbit statistics are kept for the coordinates themselves (generated=None)")
     if not isinstance(integrator, _ig._Integrator):
         raise TypeError("integrator must be one of walnuts_b200.fixedLeapFrog / adaptLeapFrogD / adaptLeapFrogR2P / "
                         "adaptYoshidaD / adaptLeapFrogFlowD / adaptImplicitMidpointD / adaptRescaledLeapFrogD")
@@ -55,9 +88,30 @@ def WALNUTS(lpFun, q0, generated=None, integrator=_ig.fixedLeapFrog, H0=0.2, ste
     single = q0.ndim == 1
     q = q0.reshape(1, -1) if single else q0
     n_chains, d = q.shape
-    name, data = _tg.resolve(lpFun, d)
     if seed is None:
         seed = _seed_from_global()
+    if devices is not None and len(devices) > 1 and n_chains > 1:
+        # several GPUs of this node: contiguous blocks of chains, one host thread per GPU
+        kw = dict(generated=generated, integrator=integrator, H0=H0, stepSizeRandScale=stepSizeRandScale, delta0=delta0,
+                  numIter=numIter, warmupIter=warmupIter, M=M, igrAux=igrAux, adaptH=adaptH, adaptHtarget=adaptHtarget,
+                  adaptDelta=adaptDelta, adaptDeltaTarget=adaptDeltaTarget, adaptDeltaQuantile=adaptDeltaQuantile,
+                  recordOrbitStats=recordOrbitStats, seed=seed, compat=compat)
+        parts = _over_devices(lambda xs, dev, off: WALNUTS(lpFun, xs, device=dev, chain_offset=off, **kw), q, devices,
+                              chain_offset)
+        return tuple(np.concatenate([p_[i] for p_ in parts]) for i in range(len(parts[0])))
+    if devices is not None and len(devices) == 1:
+        device = devices[0]
+    gen_idx = None
+    if recordOrbitStats and generated is not None:
+        # orbit minima / maxima of generated(q) over the orbit's states (WALNUTS.py:274-276,332-333,...) are kept on
+        # the GPU per coordinate; that equals min / max of generated(q) exactly when `generated` selects coordinates
+        gen_idx = _index_generator(generated, d)
+        if gen_idx is None:
+            raise NotImplementedError(
+                "recordOrbitStats with a `generated` that is not a selection of coordinates: the GPU keeps the orbit's "
+                "per-coordinate minima / maxima, which determine min / max of generated(q) only for index selections "
+                "such as gen(q) = np.array([q[0], q[1]]) (mainFunnel.py:19-20)")
+    name, data = _tg.resolve(lpFun, d)
     with ChainBatch(name, d, n_chains, mode="walnutspy", integrator=integrator.kind, H0=H0,
                     jitter=stepSizeRandScale, delta=delta0, M=M, minC=aux.minC, maxC=aux.maxC,
                     r2p_prob0=aux.R2Pprob0, seed=seed, chain_offset=chain_offset, device=device,
@@ -92,6 +146,8 @@ def WALNUTS(lpFun, q0, generated=None, integrator=_ig.fixedLeapFrog, H0=0.2, ste
     if recordOrbitStats:                                    # (dg, numIter) per chain, WALNUTS.py:183-184,724-725
         omin = np.ascontiguousarray(np.transpose(out["orbit_min"], (1, 2, 0)))
         omax = np.ascontiguousarray(np.transpose(out["orbit_max"], (1, 2, 0)))
+        if gen_idx is not None:
+            omin, omax = np.ascontiguousarray(omin[:, gen_idx]), np.ascontiguousarray(omax[:, gen_idx])
         if single:
             return samples[0], diagnostics[0], omin[0], omax[0]
         return samples, diagnostics, omin, omax
@@ -134,9 +190,19 @@ def _pkg_batch(rng, theta, logp, grad, inv_mass, macro_step, max_nuts_depth, max
 
 
 def walnuts(rng, theta_init, logp, grad, inv_mass, macro_step, max_nuts_depth, max_error, iter_warmup,
-            iter_sample, *, seed=None, device=0, compat=True, chain_offset=0):
+            iter_sample, *, seed=None, device=0, devices=None, compat=True, chain_offset=0):
     """walnuts.py:362-408.  Returns draws (iter_sample, D), or (n_chains, iter_sample, D) when
-    `theta_init` has a leading chains axis."""
+    `theta_init` has a leading chains axis.  `devices=[0, 1, ...]` shards the chains over several GPUs."""
+    th = np.asarray(theta_init, dtype=np.float64)
+    if devices is not None and len(devices) > 1 and th.ndim == 2 and th.shape[0] > 1:
+        if seed is None:
+            seed = int(rng.integers(0, 2 ** 62)) if hasattr(rng, "integers") else int(rng)
+        parts = _over_devices(lambda xs, dev, off: walnuts(rng, xs, logp, grad, inv_mass, macro_step, max_nuts_depth,
+                                                           max_error, iter_warmup, iter_sample, seed=seed, device=dev,
+                                                           compat=compat, chain_offset=off), th, devices, chain_offset)
+        return np.concatenate(parts)
+    if devices is not None and len(devices) == 1:
+        device = devices[0]
     cb, single = _pkg_batch(rng, theta_init, logp, grad, inv_mass, macro_step, max_nuts_depth, max_error,
                             seed, device, compat, chain_offset)
     with cb:

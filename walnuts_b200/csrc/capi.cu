@@ -13,57 +13,9 @@
 
 #include "../../include/walnuts_cuda.h"
 #include "wn_dispatch.cuh"
+#include "wn_handle.hpp"
 
 using namespace wn;
-
-struct wn_handle {
-  wn_config cfg;
-  cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  double* d_state = nullptr;
-  bool have_state = false;
-  double2* d_scratch = nullptr;
-  size_t scratch_bytes = 0;
-  unsigned int* d_queue = nullptr;
-  unsigned long long* d_totals = nullptr;
-  double* d_p0 = nullptr;  // inv_var | X | y(T)
-  double* d_p1 = nullptr;  // y(N)
-  double* d_p2 = nullptr;  // X^T (logreg)
-  double* d_inv_mass = nullptr;
-  double* d_H = nullptr;
-  double* d_delta = nullptr;
-  double* d_adapt_state = nullptr;   // warm-up adaptation (wn_set_adapt)
-  double* d_adapt_hist = nullptr;
-  int warmup_iter = 0, adaptH = 0, adaptDelta = 0;
-  bool adapt_exported = false;
-  double adHtarget = 0.8, adTarget = 0.6, adQuant = 0.9;
-  int maxFPiter = 30;                       // integratorAuxPar defaults, adaptiveIntegrators.py:37
-  double FPtol = 1.0e-8, gradThresh = 5.0;
-  int64_t n_p0 = 0, n_p1 = 0;
-  double tau = 1.0;
-  double inv_var_max = 1.0;
-  uint32_t iter_done = 0, iter_base = 0;   // iter_base: iter_done at creation (cfg.first_iteration - 1)
-  float last_ms = 0.f;
-  int64_t last_launches = 0;
-  unsigned long long last_tot[2] = {0, 0};
-  int num_sms = 148;
-  // grow-only device staging of the host-buffer paths (wn_run / wn_run_stats / wn_run_host_async)
-  double *o_draws = nullptr, *o_diag = nullptr, *o_lo = nullptr, *o_hi = nullptr;
-  uint64_t *o_f = nullptr, *o_b = nullptr;
-  size_t cap_draws = 0, cap_diag = 0, cap_lo = 0, cap_hi = 0;
-  std::string err;
-};
-
-static int fail(wn_handle* h, int code, const std::string& msg) {
-  if (h) h->err = msg;
-  return code;
-}
-#define CUDA_TRY(h, expr)                                                                \
-  do {                                                                                   \
-    cudaError_t _e = (expr);                                                             \
-    if (_e != cudaSuccess)                                                               \
-      return fail(h, WN_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));      \
-  } while (0)
 
 // kernel dispatch: wn_dispatch.cuh; one translation unit per kernel family (plans_*.cu) so they compile in parallel
 
@@ -93,7 +45,9 @@ static const UserTarget* user_target(int id) {
 }
 static int user_family(const wn_config& c) { return c.mode == WN_MODE_PACKAGE ? FAM_PKG : FAM_EXT; }
 
-static bool pick_plan(const wn_config& c, bool adapt, LaunchPlan& p) {
+// `general`: the call needs the kernels that carry every integrator behind the runtime kind plus the adaptation and
+// orbit-statistics code ("adapt" family): warm-up iterations, wn_run_stats with orbit buffers, adaptYoshidaD.
+static bool pick_plan(const wn_config& c, bool general, LaunchPlan& p) {
   if (c.target >= WN_TARGET_USER_BASE) {
     const UserTarget* u = user_target(c.target);
     if (!u || u->d != c.d) return false;
@@ -105,7 +59,8 @@ static bool pick_plan(const wn_config& c, bool adapt, LaunchPlan& p) {
   }
   if (c.mode == WN_MODE_PACKAGE) return wn_pick_plan_pkg(c, p);
   if (c.integrator > WN_INT_YOSHIDA) return wn_pick_plan_ext(c, p);
-  return adapt ? wn_pick_plan_adapt(c, p) : wn_pick_plan_wpy(c, p);
+  if (general || c.integrator == WN_INT_YOSHIDA) return wn_pick_plan_adapt(c, p);
+  return c.integrator == WN_INT_FIXED ? wn_pick_plan_nuts(c, p) : wn_pick_plan_wpy(c, p);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -232,6 +187,7 @@ int wn_create(const wn_config* cfg, wn_handle** out) {
 
 void wn_destroy(wn_handle* h) {
   if (!h) return;
+  wn_comm_destroy(h);
   if (h->stream) {
     cudaSetDevice(h->cfg.device);
     cudaStreamSynchronize(h->stream);
@@ -408,7 +364,7 @@ static int run_async_impl(wn_handle* h, int64_t n_iter, double* d_draws, double*
   if (c.mode == WN_MODE_PACKAGE && !h->d_inv_mass) return fail(h, WN_ESTATE, "package mode needs data key inv_mass");
   LaunchPlan p;
   const bool adapting = h->d_adapt_state != nullptr && h->iter_done < (uint32_t)h->warmup_iter;
-  if (!pick_plan(c, adapting, p)) return fail(h, WN_EUNSUPPORTED, "no CUDA kernel for this target/dimension");
+  if (!pick_plan(c, adapting || d_omin != nullptr, p)) return fail(h, WN_EUNSUPPORTED, "no CUDA kernel for this target/dimension");
   CUDA_TRY(h, cudaSetDevice(c.device));
   const UserTarget* ut = user_target(c.target);
   int occ = 0;

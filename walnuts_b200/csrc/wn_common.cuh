@@ -53,6 +53,13 @@ __device__ __forceinline__ double rng_uniform(const RngKey& k, uint32_t stream, 
   return (idx & 1u) ? u53(w.z, w.w) : u53(w.x, w.y);
 }
 
+// uniforms 2b and 2b+1 of a stream (one Philox block)
+__device__ __forceinline__ void rng_uniform_pair(const RngKey& k, uint32_t stream, uint32_t b, double& u0, double& u1) {
+  const uint4 w = philox4x32_10(make_uint4(b, k.iter, k.chain, stream), k.k0, k.k1);
+  u0 = u53(w.x, w.y);
+  u1 = u53(w.z, w.w);
+}
+
 // normal pair p of a stream: z[2p], z[2p+1]  (Box-Muller, same formula as oracle/philox.py)
 __device__ __forceinline__ void rng_normal_pair(const RngKey& k, uint32_t stream, uint32_t p,
                                                 double& z0, double& z1) {
@@ -105,6 +112,38 @@ struct Group {
           for (int ww = 1; ww < WARPS; ++ww) s += buf[ww * NV + k];
           x[k] = s;
         }
+        parity ^= 1;
+      }
+    }
+  }
+
+  // sum of one double plus OR of a small flag word over the group: the flags ride on a warp-wide integer OR
+  // (redux.sync, one instruction) and on the second slot of the shared exchange instead of a second shuffle tree
+  __device__ __forceinline__ static void sum1_flags(double& x, unsigned& flags, double* red, int& parity) {
+    if constexpr (G == 1) {
+      return;
+    } else {
+      const unsigned m = mask();
+#pragma unroll
+      for (int off = LANES / 2; off >= 1; off >>= 1) x += __shfl_xor_sync(m, x, off);
+      flags = __reduce_or_sync(m, flags);
+      if constexpr (G > 32) {
+        const int w = threadIdx.x >> 5;
+        double* buf = red + parity * (WARPS * 2);
+        if ((threadIdx.x & 31) == 0) {
+          buf[w * 2] = x;
+          buf[w * 2 + 1] = __hiloint2double(0, (int)flags);
+        }
+        __syncthreads();
+        double s = buf[0];
+        unsigned f = (unsigned)__double2loint(buf[1]);
+#pragma unroll
+        for (int ww = 1; ww < WARPS; ++ww) {
+          s += buf[ww * 2];
+          f |= (unsigned)__double2loint(buf[ww * 2 + 1]);
+        }
+        x = s;
+        flags = f;
         parity ^= 1;
       }
     }

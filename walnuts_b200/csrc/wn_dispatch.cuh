@@ -1,7 +1,9 @@
 // Kernel dispatch by (kernel family, target, dimension).  Each family -- plain WALNUTSpy transition, package
 // transition, WALNUTSpy with warm-up adaptation, extended integrators -- is instantiated in its own
-// translation unit (plans_*.cu) so that the families compile in parallel; capi.cu only sees the four
-// wn_pick_plan_* entry points.
+// translation unit (plans_*.cu) so that the families compile in parallel; capi.cu only sees the
+// wn_pick_plan_* entry points.  The plain family is split by integrator at compile time (wn_walnutspy.cuh: KSET):
+// "nuts" = fixedLeapFrog only, "wpy" = adaptLeapFrogD / adaptLeapFrogR2P only; adaptYoshidaD, the warm-up adaptation and
+// the orbit statistics run on the "adapt" family (every integrator behind the runtime kind).
 #pragma once
 #include <cstdlib>
 
@@ -18,21 +20,27 @@ struct LaunchPlan {
   bool package;
 };
 
-enum { FAM_WPY = 0, FAM_PKG = 1, FAM_ADAPT = 2, FAM_EXT = 3 };
+enum { FAM_WPY = 0, FAM_PKG = 1, FAM_ADAPT = 2, FAM_EXT = 3, FAM_NUTS = 4 };
 
 template <int G, int E2>
 using StdNormalT = DiagGaussT<G, E2, true>;
 template <int G, int E2>
 using DiagT = DiagGaussT<G, E2, false>;
 
-template <template <int, int> class T, int G, int E2, int NT, int MINB = 1, bool ADAPT = false, bool EXT = false>
+template <template <int, int> class T, int G, int E2, int NT, int MINB = 1, bool ADAPT = false, bool EXT = false,
+          int KSET = KSET_ANY, bool CTLSM = false>
 static LaunchPlan plan_wpy() {
   LaunchPlan p;
-  p.fn = (const void*)walnutspy_kernel<T, G, E2, NT, MINB, ADAPT, EXT>;
+  p.fn = (const void*)walnutspy_kernel<T, G, E2, NT, MINB, ADAPT, EXT, KSET, CTLSM>;
   p.G = G; p.E2 = E2; p.NT = NT;
-  p.smem = (size_t)(3 * 2 * E2 * NT + 2 * ((G + 31) / 32) * 8 + T<G, E2>::smem_doubles(NT)) * sizeof(double);
+  p.smem = (size_t)wpy_smem_doubles<T, G, E2, NT, ADAPT, KSET>() * sizeof(double);
   p.package = false;
   return p;
+}
+// plain family: the kernel set follows from the family (FAM_NUTS: fixedLeapFrog, FAM_WPY: D / R2P)
+template <int FAM, template <int, int> class T, int G, int E2, int NT, int MINB = 1, bool CTLSM = false>
+static LaunchPlan plan_plain() {
+  return plan_wpy<T, G, E2, NT, MINB, false, false, (FAM == FAM_NUTS) ? KSET_FIXED : KSET_ADAPT, CTLSM>();
 }
 template <template <int, int> class T, int G, int E2, int NT>
 static LaunchPlan plan_pkg() {
@@ -49,7 +57,7 @@ static LaunchPlan plan_for() {
   if constexpr (FAM == FAM_PKG) return plan_pkg<T, G, E2, NT>();
   else if constexpr (FAM == FAM_ADAPT) return plan_wpy<T, G, E2, NT, 1, true>();
   else if constexpr (FAM == FAM_EXT) return plan_wpy<T, G, E2, NT, 1, true, true>();
-  else return plan_wpy<T, G, E2, NT>();
+  else return plan_plain<FAM, T, G, E2, NT>();
 }
 
 #define WN_PICK(G, E2, NT)                                              \
@@ -83,28 +91,41 @@ static bool pick_plan_family(const wn_config& c, LaunchPlan& p) {
   switch (c.target) {
     case WN_TARGET_STD_NORMAL: return pick_generic<FAM, StdNormalT>(c.d, p);
     case WN_TARGET_DIAG_GAUSS: {
-      if constexpr (FAM == FAM_WPY) {
+      if constexpr (FAM == FAM_WPY || FAM == FAM_NUTS) {
         if (c.d > 512 && c.d <= 1024) {
           // BASELINE config 2 (d = 1000): 128 threads x 8 coordinates, 4 blocks / SM (128 registers);
           // WN_VARIANT selects the alternatives measured in DESIGN.md section 6 (tuning only)
           const char* v = getenv("WN_VARIANT");
           switch (v ? atoi(v) : 0) {
-            case 1: p = plan_wpy<DiagT, 64, 8, 64, 1>(); return true;
-            case 2: p = plan_wpy<DiagT, 128, 4, 128, 3>(); return true;
-            default: p = plan_wpy<DiagT, 128, 4, 128, 4>(); return true;
+            case 1: p = plan_plain<FAM, DiagT, 64, 8, 64, 1>(); return true;
+            case 2: p = plan_plain<FAM, DiagT, 128, 4, 128, 3>(); return true;
+            case 3: p = plan_plain<FAM, DiagT, 256, 2, 256, 2>(); return true;    // 8 warps per chain, 16 warps / SM
+            case 4: p = plan_plain<FAM, DiagT, 256, 2, 256, 4>(); return true;    // ... 32 warps / SM (64 registers)
+            case 5: p = plan_plain<FAM, DiagT, 64, 8, 64, 6>(); return true;      // 2 warps per chain, 12 warps / SM
+            case 6: p = plan_plain<FAM, DiagT, 128, 4, 128, 4>(); return true;
+            default:
+              // D / R2P: 4 blocks / SM at 124 registers; plain NUTS (level loop): 3 blocks / SM at 168 registers
+              // measured 3.41e8 against 2.62e8 grad evals/s at 128 registers (spills)
+              if constexpr (FAM == FAM_NUTS) p = plan_plain<FAM, DiagT, 128, 4, 128, 3>();
+              else p = plan_plain<FAM, DiagT, 128, 4, 128, 4>();
+              return true;
           }
         }
       }
       return pick_generic<FAM, DiagT>(c.d, p);
     }
     case WN_TARGET_FUNNEL:
-      if constexpr (FAM == FAM_WPY) {
+      if constexpr (FAM == FAM_WPY || FAM == FAM_NUTS) {
         if (c.d <= 16) {
           // BASELINE config 3 (funnel10, d = 11): 4 threads per chain (8 chains per warp), measured +30 % over
-          // one thread per chain (WN_VARIANT=1; less divergence in the cold path, 207 instead of 255 registers)
+          // one thread per chain (WN_VARIANT=1; less divergence in the cold path); the control block of every chain in
+          // shared memory (107 instead of 204 registers, twice the resident warps): 1.01e9 against 8.5e8 grad evals/s
+          // (WN_VARIANT=5: control block in registers)
           const char* v = getenv("WN_VARIANT");
-          if (v && atoi(v) == 1 && c.d <= 12) p = plan_wpy<FunnelT, 1, 6, 128, 1>();
-          else p = plan_wpy<FunnelT, 4, 2, 128, 1>();
+          const int var = v ? atoi(v) : 0;
+          if (var == 1 && c.d <= 12) p = plan_plain<FAM, FunnelT, 1, 6, 128, 1>();
+          else if (var == 5) p = plan_plain<FAM, FunnelT, 4, 2, 128, 1>();
+          else p = plan_plain<FAM, FunnelT, 4, 2, 128, 4, true>();
           return true;
         }
       }
@@ -115,14 +136,14 @@ static bool pick_plan_family(const wn_config& c, LaunchPlan& p) {
       // block-cooperative gradient (8 chains per CTA share every load of X) for the plain WALNUTSpy kernel;
       // the per-warp version serves package mode / warm-up adaptation / the other integrators and
       // WN_VARIANT=1 (comparison)
-      if constexpr (FAM == FAM_WPY) {
+      if constexpr (FAM == FAM_WPY || FAM == FAM_NUTS) {
         const char* v = getenv("WN_VARIANT");
         const int var = v ? atoi(v) : 0;
-        if (c.integrator != WN_INT_YOSHIDA && var != 1) {
+        if (var != 1) {
           // default: FP64 tensor-core gradient with TMA-staged row tiles; WN_VARIANT=2: the FMA-pipe version
-          if (var == 2 || c.d > 104) p = plan_wpy<LogRegCoopT, 32, 2, 256>();
-          else if (c.d <= 32) p = plan_wpy<LogRegMma32T, 32, 2, 256>();
-          else p = plan_wpy<LogRegMma104T, 32, 2, 256>();
+          if (var == 2 || c.d > 104) p = plan_plain<FAM, LogRegCoopT, 32, 2, 256>();
+          else if (c.d <= 32) p = plan_plain<FAM, LogRegMma32T, 32, 2, 256>();
+          else p = plan_plain<FAM, LogRegMma104T, 32, 2, 256>();
           return true;
         }
       }
@@ -136,7 +157,7 @@ static bool pick_plan_family(const wn_config& c, LaunchPlan& p) {
       if (T <= 64 * 4) {
         // 6 blocks / SM (168 registers, 12 warps) measured 9 % faster than 4 blocks at 255 registers
         // (8 blocks / SM at 128 registers: spills, same throughput)
-        if constexpr (FAM == FAM_WPY) p = plan_wpy<StockWatsonT, 64, 7, 64, 6>();
+        if constexpr (FAM == FAM_WPY || FAM == FAM_NUTS) p = plan_plain<FAM, StockWatsonT, 64, 7, 64, 6>();
         else p = plan_for<FAM, StockWatsonT, 64, 7, 64>();
         return true;
       }
@@ -153,8 +174,9 @@ static bool pick_plan_family(const wn_config& c, LaunchPlan& p) {
 
 }  // namespace wn
 
-// one definition per translation unit plans_{wpy,pkg,adapt,ext}.cu
+// one definition per translation unit plans_{wpy,nuts,pkg,adapt,ext}.cu
 bool wn_pick_plan_wpy(const wn_config& c, wn::LaunchPlan& p);
+bool wn_pick_plan_nuts(const wn_config& c, wn::LaunchPlan& p);
 bool wn_pick_plan_pkg(const wn_config& c, wn::LaunchPlan& p);
 bool wn_pick_plan_adapt(const wn_config& c, wn::LaunchPlan& p);
 bool wn_pick_plan_ext(const wn_config& c, wn::LaunchPlan& p);

@@ -1,0 +1,61 @@
+// Private to the library: the handle behind the C-ABI (include/walnuts_cuda.h), shared by capi.cu and wn_stats.cu.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+
+#include "../../include/walnuts_cuda.h"
+
+struct wn_handle {
+  wn_config cfg;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  double* d_state = nullptr;
+  bool have_state = false;
+  double2* d_scratch = nullptr;
+  size_t scratch_bytes = 0;
+  unsigned int* d_queue = nullptr;
+  unsigned long long* d_totals = nullptr;
+  double* d_p0 = nullptr;  // inv_var | X | y(T)
+  double* d_p1 = nullptr;  // y(N)
+  double* d_p2 = nullptr;  // X^T (logreg)
+  double* d_inv_mass = nullptr;
+  double* d_H = nullptr;
+  double* d_delta = nullptr;
+  double* d_adapt_state = nullptr;   // warm-up adaptation (wn_set_adapt)
+  double* d_adapt_hist = nullptr;
+  int warmup_iter = 0, adaptH = 0, adaptDelta = 0;
+  bool adapt_exported = false;
+  double adHtarget = 0.8, adTarget = 0.6, adQuant = 0.9;
+  int maxFPiter = 30;                       // integratorAuxPar defaults, adaptiveIntegrators.py:37
+  double FPtol = 1.0e-8, gradThresh = 5.0;
+  int64_t n_p0 = 0, n_p1 = 0;
+  double tau = 1.0;
+  double inv_var_max = 1.0;
+  uint32_t iter_done = 0, iter_base = 0;   // iter_base: iter_done at creation (cfg.first_iteration - 1)
+  float last_ms = 0.f;
+  int64_t last_launches = 0;
+  unsigned long long last_tot[2] = {0, 0};
+  int num_sms = 148;
+  // grow-only device staging of the host-buffer paths (wn_run / wn_run_stats / wn_run_host_async)
+  double *o_draws = nullptr, *o_diag = nullptr, *o_lo = nullptr, *o_hi = nullptr;
+  uint64_t *o_f = nullptr, *o_b = nullptr;
+  size_t cap_draws = 0, cap_diag = 0, cap_lo = 0, cap_hi = 0;
+  // cross-GPU statistics (wn_stats.cu): NCCL communicator of this handle's rank, or null
+  void* comm = nullptr;
+  int comm_rank = 0, comm_size = 1;
+  std::string err;
+};
+
+static inline int fail(wn_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  return code;
+}
+#define CUDA_TRY(h, expr)                                                                \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess)                                                               \
+      return fail(h, WN_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));      \
+  } while (0)
+

@@ -91,26 +91,66 @@ struct Ctl {
   double p2q[5], igr, maxd, Hprev;
 };
 
-template <template <int, int> class TargetTT, int G, int E2, int NT, int MINB = 1, bool ADAPT = false, bool EXT = false>
+// Kernel sets (compile-time knowledge of the integrator: smaller code, no dead search logic):
+//   KSET_ANY   every integrator behind the runtime P.kind (warm-up adaptation / extended-integrator families)
+//   KSET_FIXED fixedLeapFrog only (plain NUTS); with a whole warp per chain the per-level loop nuts_level() replaces the
+//              flat loop + state machine for the leaves
+//   KSET_ADAPT adaptLeapFrogD / adaptLeapFrogR2P only
+enum { KSET_ANY = 0, KSET_FIXED = 1, KSET_ADAPT = 2 };
+
+// left-end stack levels of the plain-NUTS level loop that live in shared memory (levels 1..NSM; deeper ones in L2 scratch)
+template <int G, int E2, int NT>
+struct NutsCfg {
+  static constexpr int NSM = 2;
+};
+template <class Target, int G, int ADAPT, int KSET>
+struct NutsFast {
+  static constexpr bool value = (KSET == KSET_FIXED) && (G >= 32) && !Target::COOP && !Target::BLOCK_LOCKSTEP && !ADAPT;
+};
+// dynamic shared memory of walnutspy_kernel in doubles: checkpoint (or the plain-NUTS left-end slots + uniform buffer),
+// reduction scratch, target
+template <template <int, int> class TargetTT, int G, int E2, int NT, bool ADAPT, int KSET>
+__host__ __device__ constexpr int wpy_smem_doubles() {
+  using Target = TargetTT<G, E2>;
+  constexpr bool NF = NutsFast<Target, G, ADAPT, KSET>::value;
+  return (NF ? 2 * NutsCfg<G, E2, NT>::NSM : 3) * 2 * E2 * NT + (NF ? 2 * NT : 0) + 2 * ((G + 31) / 32) * 8 +
+         Target::smem_doubles(NT);
+}
+
+// CTLSM: the cold control block of chains that SHARE a warp (G < 32) lives in shared memory (one copy per chain)
+// instead of per-thread registers / local memory -- fewer registers, more resident warps (G >= 32 always does).
+template <template <int, int> class TargetTT, int G, int E2, int NT, int MINB = 1, bool ADAPT = false, bool EXT = false,
+          int KSET = KSET_ANY, bool CTLSM = false>
 __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_constant__ RunParams P) {
   static_assert(!EXT || ADAPT, "EXT kernels are built with the adaptation code (inactive without wn_set_adapt)");
+  static_assert(KSET == KSET_ANY || (!ADAPT && !EXT), "specialised kernel sets exist for the plain family only");
   constexpr int E = 2 * E2;
   constexpr int GPB = NT / G;  // groups per block
   static_assert(NT % G == 0 && (G <= 32 || NT == G), "block must hold whole groups");
   using Grp = Group<G>;
   using Target = TargetTT<G, E2>;
+  constexpr bool NUTS_FAST = NutsFast<Target, G, ADAPT, KSET>::value;
+  constexpr int NSM = NutsCfg<G, E2, NT>::NSM;
+  constexpr bool LAZY = Target::LAZY_ENERGY && KSET != KSET_FIXED;   // plain NUTS consumes every step's energy
+  // integrator predicates: compile-time where the kernel set fixes them
+  auto is_fixed = [&]() -> bool { return KSET == KSET_FIXED || (KSET == KSET_ANY && P.kind == KIND_FIXED); };
+  auto is_r2p = [&]() -> bool { return KSET != KSET_FIXED && P.kind == KIND_R2P; };
 
   extern __shared__ __align__(16) double smem[];
-  double* ck = smem;                       // checkpoint: [3*E][NT]
-  double* red = smem + 3 * E * NT;         // reduction scratch (G > 32)
+  double* ck = smem;                       // checkpoint: [3*E][NT]  (NUTS_FAST: left-end slots [NSM][2][E][NT])
+  double* ubuf = smem + (NUTS_FAST ? 2 * NSM : 3) * E * NT;   // NUTS_FAST: buffered sequential uniforms, 2 per thread
+  double* red = ubuf + (NUTS_FAST ? 2 * NT : 0);              // reduction scratch (G > 32)
   __shared__ uint32_t sh_bcast;
-  __shared__ Ctl sh_ctl[(G >= 32) ? NT / 32 : 1];
+  constexpr bool CTL_SHARED = (G >= 32) || CTLSM;
+  __shared__ Ctl sh_ctl[(G >= 32) ? NT / 32 : (CTLSM ? NT / G : 1)];
+  __shared__ int sh_ktab[(G >= 32) ? NT / 32 : 1][32];   // lazy-energy passes: steps between magnitude checks, by c
   // G >= 32: one copy per warp in shared memory (volatile: every lane stores the same value, then reads it
-  // back).  G < 32: several chains share a warp, each thread keeps a private copy which the compiler is free
-  // to hold in registers / spill to local memory as it sees fit.
+  // back).  G < 32: several chains share a warp; either one shared copy per chain (CTLSM) or each thread keeps a
+  // private copy which the compiler is free to hold in registers / spill to local memory as it sees fit.
   Ctl loc_ctl;
-  using CtlRef = typename std::conditional<(G >= 32), volatile Ctl&, Ctl&>::type;
-  CtlRef C = *((G >= 32) ? &sh_ctl[threadIdx.x >> 5] : &loc_ctl);
+  using CtlRef = typename std::conditional<CTL_SHARED, volatile Ctl&, Ctl&>::type;
+  CtlRef C = *(CTL_SHARED ? &sh_ctl[(G >= 32) ? (threadIdx.x >> 5) : (threadIdx.x / G)] : &loc_ctl);
+  volatile int* ktab = sh_ktab[(G >= 32) ? (threadIdx.x >> 5) : 0];
 
   const int tid = threadIdx.x;
   const int t = tid % G;
@@ -140,7 +180,7 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
   bool rsearch = false, rexact = false, rlazyok = false;
   double rh = 0, rHref = 0, rdelta = 0, rsign = 1.0;
   unsigned long long rEv = 0;
-  const bool yoshida = (P.kind == KIND_YOSHIDA);
+  const bool yoshida = (KSET == KSET_ANY) && (P.kind == KIND_YOSHIDA);
   const unsigned long long evmul = yoshida ? 3ull : 1ull;   // gradient evaluations per micro-step
   int ysub = 0;            // Yoshida: index of the next leapfrog inside the triple
   double hh0 = 0;          // Yoshida: the micro-step size the triple is built from
@@ -150,11 +190,39 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
   int nh = 0;
   unsigned long long totF = 0, totB = 0;
 
-  auto useq = [&]() -> double {
+  // sequential scalar stream (STREAM_SEQ), draw n of the current iteration.  NUTS_FAST: the stream is counter-based,
+  // so the group computes 2 G draws ahead at once (every thread one Philox block) into a shared buffer; a draw is
+  // then one shared load instead of ten Philox rounds replicated by every warp of the chain.
+  uint4 ublk = make_uint4(0u, 0u, 0u, 0u);
+  uint32_t ublk_idx = 0xffffffffu;
+  auto ufetch = [&](uint32_t n) -> double {
     RngKey key{P.seed_lo, P.seed_hi, C.chain, C.iter};
+    if constexpr (NUTS_FAST) {
+      constexpr uint32_t UB = 2u * G;
+      double* ub = ubuf + (tid / G) * UB;
+      if ((n % UB) == 0u) {
+        if constexpr (G > 32) __syncthreads(); else __syncwarp();
+        double u0, u1;
+        rng_uniform_pair(key, STREAM_SEQ, (n >> 1) + (uint32_t)t, u0, u1);
+        ub[2 * t] = u0;
+        ub[2 * t + 1] = u1;
+        if constexpr (G > 32) __syncthreads(); else __syncwarp();
+      }
+      return ub[n % UB];
+    } else {
+      // consecutive draws 2b, 2b + 1 share a Philox block: keep the last block (the stream is consumed in order)
+      const uint32_t b = n >> 1;
+      if (b != ublk_idx) {
+        ublk = philox4x32_10(make_uint4(b, key.iter, key.chain, STREAM_SEQ), key.k0, key.k1);
+        ublk_idx = b;
+      }
+      return (n & 1u) ? u53(ublk.z, ublk.w) : u53(ublk.x, ublk.y);
+    }
+  };
+  auto useq = [&]() -> double {
     const uint32_t n = C.nseq;
     C.nseq = n + 1;
-    return rng_uniform(key, STREAM_SEQ, n);
+    return ufetch(n);
   };
   auto jit = [&](double u) -> double {
     const double lo = C.jlo;
@@ -271,14 +339,14 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
   };
   auto start_pass = [&](int cc) {
     steps_left = (yoshida ? 3u : 1u) << cc;
-    hh = ldexp(rh, -cc);
+    hh = rh * __longlong_as_double((long long)(1023 - cc) << 52);   // rh 2^-cc, exact (cc <= 30, rh normal)
     ha = 0.5 * hh;
     hh0 = hh;
     ysub = 0;
     expmax = 0;
     smax = 0;
     umax = 0;
-    if constexpr (Target::LAZY_ENERGY) {
+    if constexpr (LAZY) {
       lazy = rlazyok && !rexact && (cc >= 2) && !trackH && !yoshida;
       if (lazy) {
         // the pass starts from a bounded state (registers = checkpoint up to the sign of v, which the two
@@ -286,14 +354,17 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
         if (ckTracked) { smax = ckS; umax = ckU; }
         else { track_state(); ckS = smax; ckU = umax; ckTracked = true; }
         since = 0;
-        // One leapfrog step amplifies max(|q|,|v|) by at most Gamma (target-specific bound); checked
-        // states are below 2^300, so up to floor(180 / log2 Gamma) steps may pass between checks while
-        // every skipped energy stays finite (< 2^480 magnitudes).
-        // (two steps of the budget are reserved for the half kick that the merged-kick loop carries in v)
-        // log2 Gamma is bounded from above by the exponent field (Gamma >= 1): integer arithmetic only
-        const int lg = ((__double2hiint(target.step_growth(hh)) >> 20) & 0x7ff) - 1022;
-        lazyK = (lg * 66 <= 180) ? 64 : ((int)__fdividef(180.0f, (float)lg) - 2);
-        lazyK &= ~1;
+        // One leapfrog step amplifies max(|q|,|v|) by at most Gamma (target-specific bound); checked states are
+        // below 2^300, so up to floor(170 / log2 Gamma) steps may pass between checks while every skipped energy
+        // stays finite: magnitudes < 2^470, terms q^2 s < 2^(940 + 60), their sum over d <= 2^11 coordinates < 2^1011.  Gamma grows with the step, so the interval is tabulated per c once per
+        // iteration for the LARGEST jittered macro step (ST_ITER: ktab), a conservative bound for every macro step.
+        if constexpr (G >= 32) {
+          lazyK = ktab[cc];
+        } else {
+          const int lg = ((__double2hiint(target.step_growth(hh)) >> 20) & 0x7ff) - 1022;
+          lazyK = (lg * 66 <= 170) ? 64 : ((int)__fdividef(170.0f, (float)lg) - 2);
+          lazyK &= ~1;
+        }
         if (lazyK < 2) lazy = false;
       }
     }
@@ -303,22 +374,24 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
     }
   };
   // U-turn criterion, reference WALNUTS.py:95-97; (ql, vl) read from scratch, the other state is the
-  // register-resident end (q, xi*v).  Orientation: minus end = more backward state.
+  // register-resident end (q, xi*v).  Orientation: minus end = more backward state, tmp = qp - qm = xi (q - ql).
+  // The signs are factored out of the sums: (xi v).(xi (q - ql)) = v.(q - ql) term by term, and
+  // vl.(xi (q - ql)) = xi (vl.(q - ql)) because negating every product negates every partial sum exactly
+  // (round-to-nearest is symmetric) -- bit-identical to the signed form at 3 instead of 5 FP64 instructions per
+  // coordinate.
   auto uturn_vs = [&](int viq, int viv) -> bool {
-    const double xi = C.xi;
     double x[2] = {0.0, 0.0};
 #pragma unroll
     for (int e2 = 0; e2 < E2; ++e2) {
       const double2 ql = *sc(viq, e2), vl = *sc(viv, e2);
-      // forward level: plus = current, minus = left;  backward level: minus = current, plus = left
-      const double t0 = xi * (q[2 * e2] - ql.x), t1 = xi * (q[2 * e2 + 1] - ql.y);   // qp - qm
-      x[0] = fma(xi * v[2 * e2], t0, x[0]);
-      x[0] = fma(xi * v[2 * e2 + 1], t1, x[0]);  // v_cur(fwd time) . tmp
+      const double t0 = q[2 * e2] - ql.x, t1 = q[2 * e2 + 1] - ql.y;
+      x[0] = fma(v[2 * e2], t0, x[0]);
+      x[0] = fma(v[2 * e2 + 1], t1, x[0]);  // v_cur(fwd time) . tmp
       x[1] = fma(vl.x, t0, x[1]);
-      x[1] = fma(vl.y, t1, x[1]);  // v_left . tmp
+      x[1] = fma(vl.y, t1, x[1]);           // xi (v_left . tmp)
     }
     Grp::template sum<2>(x, red, parity);
-    return (x[0] < 0.0) || (x[1] < 0.0);
+    return (x[0] < 0.0) || (C.xi * x[1] < 0.0);
   };
   // one leapfrog micro-step on the registers; reference adaptiveIntegrators.py:79-84 (:50-55 fixed)
   auto micro_step = [&](bool kick1 = true) {
@@ -347,7 +420,7 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
   // micro step <= 2^10 one leapfrog step amplifies |q|, |v| by at most 2^142 in the worst case; start_pass() derives the actual per-step bound Gamma and the number of steps
   // that may pass between two checks.
   auto micro_step_lazy = [&]() {
-    if constexpr (Target::LAZY_ENERGY) {
+    if constexpr (LAZY) {
 #pragma unroll
       for (int e = 0; e < E; ++e) {
         v[e] = fma(ha, g[e], v[e]);
@@ -376,6 +449,203 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
 
   uint32_t coop_phase = 0;   // COOP targets: phase bits of the staging mbarriers
   int st = ST_CHAIN;
+  // ===================== plain NUTS (fixedLeapFrog), whole warps per chain: one doubling level ======================
+  // Replaces ST_MACRO -> ST_RUN -> ST_PASS_END -> ST_LEAF of the flat loop for the n_new = 2^level leaves of a level
+  // (reference WALNUTS.py:296-368 for level 0, :392-587 for the leaf pairs; adaptiveIntegrators.py:49-59 per leaf).
+  // With lwt = 0, If = Ib = c = 0 for every leaf the bookkeeping collapses, so the level runs as a register-resident
+  // loop over LEAF PAIRS (the unit of the reference's plan rows with |a - b| = 1, :394): both leaves are integrated,
+  // then ONE group reduction delivers both energies and the two dot products of the pair's own U-turn check (span 2);
+  // the bookkeeping of the two leaves follows in the reference's order, with early exit (the second leaf's integration
+  // was speculative if the first one force-rejects -- its results are then simply not applied).  The left end of a
+  // pending dyadic level <= NSM lives in shared memory (each thread reads back only what it wrote: no barrier), deeper
+  // ones in the L2-resident scratch; a leaf m = 3 (mod 4) is only ever the left end of its own pair, i.e. half of all
+  // left ends never leave the SM.  Sequential uniforms come from the buffered stream (ufetch).
+  auto nuts_level = [&]() {
+    if constexpr (NUTS_FAST) {
+      const int level = C.level, side = C.side;
+      const double xi = C.xi, H0 = C.H0;
+      const uint32_t n_new = C.n_new;
+      const double jlo = C.jlo, jhi = C.jhi;
+      auto jitl = [&](double u) -> double { return __dadd_rn(jlo, __dmul_rn(__dadd_rn(jhi, -jlo), u)); };
+      uint32_t nseq = C.nseq;
+      double WnewSum = 0.0;
+      double tl = side ? C.timeLen1 : C.timeLen0;
+      int mi = side ? C.maxInt1 : C.maxInt0;
+      const int dstep = side ? -1 : 1;
+      double endH = side ? C.endH1 : C.endH0;
+      double orbitLen = C.orbitLen;
+      int sN = C.sN, sHnan = C.sHnan;
+      double sHmax = C.sHmax, sHmin = C.sHmin;
+      int L_ = C.L_, candValid = 0, stop999 = 0;
+      double indexStat = C.indexStat;
+      const int pvec = V_PROP0 + (C.propCur ^ 1);
+      uint32_t nleaf = 0;
+      unsigned long long nF = 0;
+      int out = 0;   // 0: level complete, 1: forced reject, 2: sub-U-turn
+      // left-end slot `lvl` (>= 1): (q, xi v) in forward-time convention, as the L2 stack of the flat loop
+      auto put_left = [&](int lvl) {
+        if (lvl <= NSM) {
+          double* b = ck + (size_t)(lvl - 1) * 2 * E * NT + tid;
+#pragma unroll
+          for (int e = 0; e < E; ++e) { b[e * NT] = q[e]; b[(E + e) * NT] = xi * v[e]; }
+        } else {
+#pragma unroll
+          for (int e2 = 0; e2 < E2; ++e2) {
+            *sc(V_STACK + 2 * lvl, e2) = make_double2(q[2 * e2], q[2 * e2 + 1]);
+            *sc(V_STACK + 2 * lvl + 1, e2) = make_double2(xi * v[2 * e2], xi * v[2 * e2 + 1]);
+          }
+        }
+      };
+      // partial sums of the U-turn criterion (WALNUTS.py:95-97) between the registers and left-end slot `lvl`:
+      // a = v . (q - ql), b = vl . (q - ql)   (signs factored out, see uturn_vs)
+      auto dots_left = [&](int lvl, double& a, double& b) {
+        double a0 = 0.0, b0 = 0.0;
+        if (lvl <= NSM) {
+          const double* p = ck + (size_t)(lvl - 1) * 2 * E * NT + tid;
+#pragma unroll
+          for (int e = 0; e < E; ++e) {
+            const double tt = q[e] - p[e * NT];
+            a0 = fma(v[e], tt, a0);
+            b0 = fma(p[(E + e) * NT], tt, b0);
+          }
+        } else {
+#pragma unroll
+          for (int e2 = 0; e2 < E2; ++e2) {
+            const double2 ql = *sc(V_STACK + 2 * lvl, e2), vl = *sc(V_STACK + 2 * lvl + 1, e2);
+            const double t0 = q[2 * e2] - ql.x, t1 = q[2 * e2 + 1] - ql.y;
+            a0 = fma(v[2 * e2], t0, a0);
+            a0 = fma(v[2 * e2 + 1], t1, a0);
+            b0 = fma(vl.x, t0, b0);
+            b0 = fma(vl.y, t1, b0);
+          }
+        }
+        a = a0;
+        b = b0;
+      };
+      // proposal slot <- left-end slot `lvl` (the picked state is the first leaf of the pair)
+      auto prop_from_left = [&](int lvl) {
+        if (lvl <= NSM) {
+          const double* p = ck + (size_t)(lvl - 1) * 2 * E * NT + tid;
+#pragma unroll
+          for (int e2 = 0; e2 < E2; ++e2) *sc(pvec, e2) = make_double2(p[(2 * e2) * NT], p[(2 * e2 + 1) * NT]);
+        } else {
+#pragma unroll
+          for (int e2 = 0; e2 < E2; ++e2) *sc(pvec, e2) = *sc(V_STACK + 2 * lvl, e2);
+        }
+      };
+      // bookkeeping of one leaf with energy Hl and step h (WALNUTS.py:302-328 / :401-429 / :440-467 and the forward
+      // twins); returns false on a forced reject.  `pick` tells the caller to store the proposal.
+      auto leaf_book = [&](double Hl, double h, bool& pick) -> bool {
+        ++nleaf;
+        ++nF;
+        mi += dstep;
+        tl = tl + h;
+        endH = Hl;
+        ++sN;
+        if (Hl != Hl) sHnan = 1;
+        else { sHmax = fmax(sHmax, Hl); sHmin = fmin(sHmin, Hl); }
+        pick = false;
+        if (!finite_d(Hl)) {                                     // :316,350,414,457,501,544 (quirks A14 ii, iii)
+          if (level == 0 || (nleaf & 1u)) stop999 = 1;
+          return false;
+        }
+        const double Wnew = exp(-Hl + H0);                       // lwtSum = 0 for fixedLeapFrog (:321-322,...)
+        if (level == 0) {
+          WnewSum = Wnew;
+          pick = true;                                           // :326,359
+        } else {
+          const double ws = WnewSum + Wnew;
+          WnewSum = ws;
+          if (ws > WN_WT_SUM_THRESH) pick = ufetch(nseq++) < Wnew / ws;   // :426,464,512,554
+          orbitLen = orbitLen + h;                               // :432,...
+        }
+        if (pick) {
+          candValid = 1;
+          L_ = mi;
+          indexStat = side ? -tl : tl;
+        }
+        return true;
+      };
+      do {
+        const uint32_t nA = nleaf + 1u;
+        const double hA = jitl(ufetch(nseq++));                  // :298 / :395 (two draws per leaf pair)
+        double hB = 0.0;
+        if (level == 0) orbitLen = orbitLen + hA;                // :300
+        else hB = jitl(ufetch(nseq++));
+        hh = hA;
+        ha = 0.5 * hA;
+        micro_step();
+        double x[4] = {hp, 0.0, 0.0, 0.0};
+        int lvlA = 0;
+        if (level > 0) {
+          lvlA = (nA == 1u) ? level : (__ffs(nA - 1u) - 1);
+          put_left(lvlA);
+          hh = hB;
+          ha = 0.5 * hB;
+          micro_step();
+          x[1] = hp;
+          dots_left(lvlA, x[2], x[3]);
+        }
+        Grp::template sum<4>(x, red, parity);
+        bool pick;
+        if (!leaf_book(x[0], hA, pick)) { out = 1; break; }
+        if (pick) {
+          if (level == 0) {
+#pragma unroll
+            for (int e2 = 0; e2 < E2; ++e2) *sc(pvec, e2) = make_double2(q[2 * e2], q[2 * e2 + 1]);
+          } else {
+            prop_from_left(lvlA);
+          }
+        }
+        if (level == 0) break;
+        if (!leaf_book(x[1], hB, pick)) { out = 1; break; }
+        if (pick) {
+#pragma unroll
+          for (int e2 = 0; e2 < E2; ++e2) *sc(pvec, e2) = make_double2(q[2 * e2], q[2 * e2 + 1]);
+        }
+        // post-order sub-U-turn checks ending at this leaf (WALNUTS.py:22-41 plan; :479,568,582)
+        bool sub = (x[2] < 0.0) || (xi * x[3] < 0.0);
+        for (int sp = 2; !sub && sp <= level && (nleaf & ((1u << sp) - 1u)) == 0u; ++sp) {
+          const uint32_t m = nleaf - (1u << sp) + 1u;
+          const int lvl = (m == 1u) ? level : (__ffs(m - 1u) - 1);
+          double y[2];
+          dots_left(lvl, y[0], y[1]);
+          Grp::template sum<2>(y, red, parity);
+          sub = (y[0] < 0.0) || (xi * y[1] < 0.0);
+        }
+        if (sub) { out = 2; break; }
+      } while (nleaf < n_new);
+      // ---- write the level's state back for the shared handlers (level end / iteration end) ----
+      C.nseq = nseq;
+      C.nleaf = nleaf;
+      C.WnewSum = WnewSum;
+      if (side) { C.timeLen1 = tl; C.maxInt1 = mi; C.endH1 = endH; }
+      else { C.timeLen0 = tl; C.maxInt0 = mi; C.endH0 = endH; }
+      C.orbitLen = orbitLen;
+      C.sN = sN; C.sNz = sN;                                     // If = 0 for every leaf
+      C.sMinIf = 0; C.sMaxIf = 0; C.sMinC = 0; C.sMaxC = 0; C.sMinL = 0.0; C.sMaxL = 0.0;
+      C.sHmax = sHmax; C.sHmin = sHmin; C.sHnan = sHnan;
+      C.nF = C.nF + nF;
+      C.L_ = L_;
+      C.indexStat = indexStat;
+      C.candValid = candValid;
+      if (out == 1) {
+        C.forced = 1;
+        if (stop999) C.stopCode = 999;
+        st = ST_ITER_END;
+      } else if (out == 2) {                                     // :597-605
+        C.candValid = 0;
+        C.L_ = C.Lold;
+        C.indexStat = C.indexStatOld;
+        C.NdS = level;
+        C.NdC = level + 1;
+        C.stopCode = 5;
+        st = ST_ITER_END;
+      } else {
+        st = ST_LEVEL_END;
+      }
+    }
+  };
   for (;;) {
     if constexpr (Target::BLOCK_LOCKSTEP) {
       // chains of a block evaluate their gradients in lock-step (shared data tiles stay hot in L1);
@@ -410,7 +680,7 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
         if (--steps_left != 0u) continue;
         st = ST_PASS_END;
       }
-    } else if (st == ST_RUN) {
+    } else if (!NUTS_FAST && st == ST_RUN) {
       if (yoshida) {
         // one leapfrog of the 4th-order triple (coefficients firstLast, middle, firstLast, :157-173); the
         // energy (Hams[i], :175) and its finiteness only count after the third
@@ -438,21 +708,27 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
         ++nh;
         --steps_left;
         if (nh == 4 || steps_left == 0u) flush_hist();
-      } else if (Target::LAZY_ENERGY && lazy && steps_left >= 3u) {
-        if constexpr (Target::LAZY_ENERGY && G >= 32 && !Target::BLOCK_LOCKSTEP) {
+      } else if (LAZY && lazy && steps_left >= 3u) {
+        if constexpr (LAZY && G >= 32 && !Target::BLOCK_LOCKSTEP) {
           // the whole warp follows one chain: stay in a tight loop for the skipped-energy steps (merged kicks),
           // then finish the pass with the one step whose energy is consumed
           double kc[E];
           target.kick_coeffs(hh, kc);
 #pragma unroll
           for (int e = 0; e < E; ++e) v[e] = fma(ha, g[e], v[e]);
+          // blocks of up to lazyK (even) steps between two magnitude checks; one or two steps are left for the end
+          uint32_t n = (steps_left - 1u) & ~1u;
+          steps_left -= n;
           do {
-            drift_kick(kc);
-            drift_kick(kc);
-            steps_left -= 2u;
-            since += 2;
-            if (since >= lazyK) { track_state(); since = 0; }
-          } while (steps_left >= 3u);
+            const uint32_t m = min(n, (uint32_t)lazyK);
+            n -= m;
+#pragma unroll 2
+            for (uint32_t i = 0; i < m; i += 2u) {
+              drift_kick(kc);
+              drift_kick(kc);
+            }
+            if (n) track_state();
+          } while (n);
           if (steps_left == 2u) drift_kick(kc);
           micro_step(false);
           steps_left = 0u;
@@ -463,7 +739,7 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
           since += 2;
           if (since >= lazyK) { track_state(); since = 0; }
         }
-      } else if (Target::LAZY_ENERGY && lazy && steps_left == 2u) {
+      } else if (LAZY && lazy && steps_left == 2u) {
         micro_step_lazy();
         micro_step();
         steps_left = 0u;
@@ -483,14 +759,17 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
     // a chain from the end of a pass to the start of the next one, and the chains that share a warp (G < 32) run
     // each handler TOGETHER instead of serialising a switch: pass end -> leaf -> level end -> iteration end ->
     // next chain -> iteration setup -> level start -> macro-step start -> (hot loop).
-    if (st == ST_PASS_END) do {  // a pass of 2^c micro-steps finished
+    if constexpr (NUTS_FAST) {
+      if (st == ST_MACRO) nuts_level();
+    }
+    if (!NUTS_FAST && st == ST_PASS_END) do {  // a pass of 2^c micro-steps finished
       const bool unbounded = (smax & 0x7ff00000) >= LAZY_LIMIT ||
                              ((umax & 0x80000000u) && (int)(umax & 0x7ff00000u) >= LAZY_LIMIT);
-      double x[2] = {hp, ((expmax == 0x7ff00000) ? 1.0 : 0.0) + (unbounded ? 1024.0 : 0.0)};
-      Grp::template sum<2>(x, red, parity);
-      const double Hend = x[0];
-      const bool redo_exact = Target::LAZY_ENERGY && x[1] >= 1024.0;
-      const bool anybad = x[1] != 0.0;
+      double Hend = hp;
+      unsigned pflags = ((expmax == 0x7ff00000) ? 1u : 0u) | (unbounded ? 2u : 0u);
+      Grp::sum1_flags(Hend, pflags, red, parity);
+      const bool redo_exact = LAZY && (pflags & 2u);
+      const bool anybad = pflags != 0u;
       if (rsearch && !redo_exact) {
         // fast path of the search (adaptiveIntegrators.py:69-94, 111-132): attempt failed -> next c
         const bool ok = !anybad && fabs(rHref - Hend) < rdelta;
@@ -528,7 +807,7 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
       if (phase == PH_FWD) {
         C.nF = C.nF + (evmul << c);
         const bool ok = !anybad && fabs(C.Ham0 - Hend) < C.delta;   // adaptiveIntegrators.py:87-92
-        if (!(P.kind == KIND_FIXED || ok || c == P.maxC)) {
+        if (!(is_fixed() || ok || c == P.maxC)) {
           ++c;
           C.c = c;
           rc = c;
@@ -540,7 +819,7 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
         C.If = c;
         C.cSim = c;
         C.lwtf = 0.0;
-        if (P.kind == KIND_R2P) {
+        if (is_r2p()) {
           if (useq() < P.p0) {              // adaptiveIntegrators.py:392
             C.lwtf = P.log_p0;
           } else {                          // :400-424 redo at If+1
@@ -562,7 +841,7 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
         C.Hfwd = Hend;
         if constexpr (ADAPT) {
           if (C.warm && P.adaptH) {
-            if (P.kind == KIND_FIXED) {      // adaptiveIntegrators.py:59
+            if (is_fixed()) {      // adaptiveIntegrators.py:59
               const double ad = fabs(C.Ham0 - Hend);
               C.igr = rh * pow((ad > 1.0e-10) ? ad : 1.0e-10, -1.0 / 3.0);
             } else {                         // :101,399,424 (last forward pass)
@@ -572,7 +851,7 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
           }
           trackH = false;
         }
-        if (P.kind == KIND_FIXED) {
+        if (is_fixed()) {
           C.Ib = 0;
           C.lwt = 0.0;
           st = ST_LEAF;
@@ -580,7 +859,7 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
         }
         const int If = C.If, cSim = C.cSim;
         int maxTry, Ib;
-        if (P.kind != KIND_R2P || cSim == If) { maxTry = If - 1; Ib = If; }   // :104-111 / :195-202 / :430-433
+        if (!is_r2p() || cSim == If) { maxTry = If - 1; Ib = If; }   // :104-111 / :195-202 / :430-433
         else { maxTry = P.maxC; Ib = P.maxC; }                              // :434-437
         C.maxTry = maxTry;
         C.Ib = Ib;
@@ -614,7 +893,7 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
       // macro step complete
       {
         const int If = C.If, Ib = C.Ib, cSim = C.cSim;
-        if (P.kind != KIND_R2P) {
+        if (!is_r2p()) {
           C.lwt = (If != Ib) ? WN_LOG_ZERO : 0.0;                  // :136, :239
         } else {
           double lwtb = WN_LOG_ZERO;                               // :467-471
@@ -627,7 +906,7 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
       st = ST_LEAF;
       break;
     } while (0);
-    if (st == ST_LEAF) do {  // driver bookkeeping after a macro step, WALNUTS.py:302-368,398-570
+    if (!NUTS_FAST && st == ST_LEAF) do {  // driver bookkeeping after a macro step, WALNUTS.py:302-368,398-570
       if constexpr (ADAPT) {
         if (C.warm && P.adaptH) p2_push(log(C.igr));    // :313,347,411,454,498,541
       }
@@ -640,7 +919,7 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
       else { C.maxInt0 = idx; C.timeLen0 = tl; C.endH0 = Hfwd; }
       {  // running statistics over used steps
         const int If = C.If, Ib = C.Ib;
-        const int cs = (P.kind == KIND_FIXED) ? 0 : C.cSim;
+        const int cs = is_fixed() ? 0 : C.cSim;
         if (C.sN == 0) {
           C.sMinIf = If; C.sMaxIf = If;
           C.sMinC = cs; C.sMaxC = cs;
@@ -871,7 +1150,7 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
       if (t == 0) {
         if (P.nevalF) P.nevalF[cidx] = cf;
         if (P.nevalB) P.nevalB[cidx] = cbk;
-        if constexpr (ADAPT) if (!EXT || P.adapt_state) {
+        if constexpr (ADAPT) if (P.adapt_state) {
           double* as = P.adapt_state + (size_t)cidx * WN_ADAPT_STRIDE;
           as[0] = C.Hbig; as[1] = C.delta; as[2] = (double)C.p2npush;
 #pragma unroll
@@ -901,7 +1180,7 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
       C.Hbig = P.Hstep ? P.Hstep[cidx] : P.H0;
       C.delta = P.delta ? P.delta[cidx] : P.delta0;
       if constexpr (ADAPT) {
-        if (!EXT || P.adapt_state) {
+        if (P.adapt_state) {
         const double* as = P.adapt_state + (size_t)cidx * WN_ADAPT_STRIDE;
         C.Hbig = as[0];
         C.delta = as[1];
@@ -922,16 +1201,33 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
       RngKey key{P.seed_lo, P.seed_hi, C.chain, P.iter0 + (uint32_t)C.it};
       C.iter = key.iter;
       C.nseq = 0;
+      ublk_idx = 0xffffffffu;
       {
         const double Hbig = C.Hbig;
         C.jlo = __dmul_rn(Hbig, __dadd_rn(1.0, -P.jitter));   // WALNUTS.py:298
         C.jhi = __dmul_rn(Hbig, __dadd_rn(1.0, P.jitter));
       }
-      if constexpr (ADAPT) C.warm = ((!EXT || P.adapt_state) && key.iter <= (uint32_t)P.warmup_iter) ? 1 : 0;   // :209
+      if constexpr (LAZY && G >= 32) {
+        // steps between two magnitude checks of a skipped-energy pass at c = t (see start_pass); two steps of the
+        // budget are reserved for the half kick that the merged-kick loop carries in v; log2 Gamma is bounded
+        // from above by the exponent field (Gamma >= 1): integer arithmetic only
+        {
+          const int cc = tid & 31;
+          const double hmax = C.jhi * __longlong_as_double((long long)(1023 - cc) << 52);
+          const int lg = ((__double2hiint(target.step_growth(hmax)) >> 20) & 0x7ff) - 1022;
+          int k = (lg * 66 <= 170) ? 64 : ((int)__fdividef(170.0f, (float)lg) - 2);
+          k &= ~1;
+          ktab[cc] = (k < 2) ? 0 : k;
+        }
+        __syncwarp();
+      }
+      if constexpr (ADAPT) C.warm = (P.adapt_state && key.iter <= (uint32_t)P.warmup_iter) ? 1 : 0;   // :209
       uint32_t dirbits = 0;
-      for (int k = 0; k < P.M; ++k) {
-        const double u = rng_uniform(key, STREAM_DIR, (uint32_t)k);   // B = floor(U(0,2)), :216
-        dirbits |= (u >= 0.5 ? 1u : 0u) << k;
+      for (int k = 0; k < P.M; k += 2) {                                // B = floor(U(0,2)), :216
+        double u0, u1;                                                  // one Philox block = uniforms k, k + 1
+        rng_uniform_pair(key, STREAM_DIR, (uint32_t)k >> 1, u0, u1);
+        dirbits |= (u0 >= 0.5 ? 1u : 0u) << k;
+        if (k + 1 < P.M) dirbits |= (u1 >= 0.5 ? 1u : 0u) << (k + 1);
       }
       C.dirbits = dirbits;
       double x[1];
@@ -1045,7 +1341,7 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
       st = ST_MACRO;
       break;
     } while (0);
-    if (st == ST_MACRO) do {  // start one macro step from the active end
+    if (!NUTS_FAST && st == ST_MACRO) do {  // start one macro step from the active end
       const uint32_t nleaf = C.nleaf + 1u;
       C.nleaf = nleaf;
       double h;
@@ -1324,15 +1620,15 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
         break;
       }
       C.phase = PH_FWD;
-      const int c0 = (P.kind == KIND_FIXED) ? 0 : P.minC;
+      const int c0 = is_fixed() ? 0 : P.minC;
       C.c = c0;
       rh = h; rc = c0; rlim = P.maxC; rHref = Ham0; rdelta = C.delta; rsign = 1.0;
-      rsearch = (P.kind != KIND_FIXED);
+      rsearch = !is_fixed();
       rexact = false;
       rEv = 0;
-      if constexpr (ADAPT) trackH = C.warm && P.adaptH && (P.kind != KIND_FIXED);
-      if constexpr (Target::LAZY_ENERGY) rlazyok = target.lazy_ok && (C.jhi <= 1024.0);
-      if (P.kind != KIND_FIXED) save_ck();   // S = start state (integration convention)
+      if constexpr (ADAPT) trackH = C.warm && P.adaptH && !is_fixed();
+      if constexpr (LAZY) rlazyok = target.lazy_ok && (C.jhi <= 1024.0);
+      if (!is_fixed()) save_ck();   // S = start state (integration convention)
       C.wIntact = 1;
       start_pass(c0);
       st = ST_RUN;

@@ -233,9 +233,49 @@ class ChainBatch:
         self._check(self._lib.wn_moments(self._h, pm, pv), "wn_moments")
         return mean, var
 
+    # -- cross-GPU statistics (NCCL inside the library) -------------------------------------------
+    def comm_init_rank(self, nranks, rank, unique_id):
+        """Join the NCCL communicator of a multi-process run (one rank per GPU); `unique_id` = the 128 bytes that
+        rank 0 obtained from comm_unique_id() and shipped to every rank."""
+        buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id))
+        self._check(self._lib.wn_comm_init_rank(self._h, int(nranks), int(rank), buf), "wn_comm_init_rank")
+
+    def ess_rhat(self, draws, split=True):
+        """(ess [dg], rhat [dg]): bulk ESS and split-R-hat of draws (n_iter, n_chains, dg) -- numpy or a torch CUDA
+        tensor -- computed on the device; pooled over all ranks when a communicator is attached (one all-gather)."""
+        n_iter, n_chains, dg = (int(x) for x in draws.shape)
+        p, dev = _ptr(draws, n_iter * n_chains * dg, what="ess_rhat(draws)")
+        ess, rhat = np.empty(dg), np.empty(dg)
+        rc = self._lib.wn_ess_rhat(self._h, p, n_iter, n_chains, dg, dev, int(bool(split)), _ptr(ess)[0], _ptr(rhat)[0])
+        self._check(rc, "wn_ess_rhat")
+        return ess, rhat
+
+    def moments_all(self):
+        """moments() over the chains of every rank of the communicator."""
+        mean, var = np.empty(self.d), np.empty(self.d)
+        self._check(self._lib.wn_moments_all(self._h, _ptr(mean)[0], _ptr(var)[0]), "wn_moments_all")
+        return mean, var
+
     @property
     def stream(self):
         return self._lib.wn_stream(self._h)
+
+
+def comm_unique_id():
+    """128-byte NCCL unique id (rank 0 of a multi-process run creates it and ships it to the other ranks)."""
+    buf = (C.c_char * 128)()
+    rc = _ffi.load().wn_comm_unique_id(buf)
+    if rc != 0:
+        raise WalnutsError(f"wn_comm_unique_id: {_ffi.ERRORS.get(rc, rc)} (is libnccl.so.2 available?)")
+    return bytes(buf)
+
+
+def comm_init_all(batches):
+    """One process driving several GPUs: attach a communicator to one ChainBatch per device."""
+    arr = (C.c_void_p * len(batches))(*[b._h for b in batches])
+    rc = _ffi.load().wn_comm_init_all(arr, len(batches))
+    if rc != 0:
+        raise WalnutsError(f"wn_comm_init_all: {_ffi.ERRORS.get(rc, rc)}: {batches[0]._err()}")
 
 
 def fp64_peak(device=0):
