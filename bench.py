@@ -169,8 +169,7 @@ class ClockSampler:
 def _cpu_worker(args):
     """Run transitions of chain `chain` of workload `name` for ~`budget` seconds (at least `min_tr` timed
     transitions after `warm` untimed ones, at most `max_tr`).  Returns (evals, seconds, transitions)."""
-    name, chain, budget, min_tr, max_tr, warm = args
-    os.environ["OMP_NUM_THREADS"] = "1"
+    name, chain, budget, min_tr, max_tr, warm, impl = args
     spec = WORKLOADS[name]
     q0, data = make_inputs(spec, chain + 1, 0)
     q = q0[chain]
@@ -205,11 +204,19 @@ def _cpu_worker(args):
         else:
             lp = ot.std_normal
         kind = {"fixed": wo.FIXED, "D": wo.ADAPT_D, "R2P": wo.ADAPT_R2P}[spec["integrator"]]
+        ref_name = {"fixed": "fixedLeapFrog", "D": "adaptLeapFrogD", "R2P": "adaptLeapFrogR2P"}[spec["integrator"]]
+        if impl == "reference":
+            from oracle import ref_loader        # the REAL WALNUTS.py / adaptiveIntegrators.py (oracle/_ref or /root/reference)
         it = 1
         while True:
             t0 = time.perf_counter()
-            s, dg = wo.WALNUTS(lp, q, integrator=kind, H0=spec["H0"], delta0=spec["delta"], numIter=1, M=spec["M"],
-                               igrAux=wo.AuxPar(spec["minC"], spec["maxC"]), seed=SEED, chain=chain, first_iteration=it)
+            if impl == "reference":
+                s, dg = ref_loader.run_walnutspy(lp, q, ref_name, spec["H0"], spec["delta"], 1, spec["M"], spec["minC"],
+                                                 spec["maxC"], seed=SEED, chain=chain, first_iteration=it)
+            else:
+                s, dg = wo.WALNUTS(lp, q, integrator=kind, H0=spec["H0"], delta0=spec["delta"], numIter=1, M=spec["M"],
+                                   igrAux=wo.AuxPar(spec["minC"], spec["maxC"]), seed=SEED, chain=chain,
+                                   first_iteration=it)
             dt = time.perf_counter() - t0
             q = s[:, -1]
             it += 1
@@ -237,18 +244,29 @@ def _pool(cores):
     return _POOL
 
 
-def cpu_baseline(name="c2", budget=12.0, min_tr=1, max_tr=10 ** 9, warm=0, cores=None):
-    """Gradient evals/sec of the reference algorithm (numpy port) with every host core busy on its own chain:
-    the sum over cores of (evaluations / busy seconds)."""
+def reference_available():
+    """The real reference's modules are importable here (the build container, or a copy staged by oracle/stage_ref.py)."""
+    try:
+        from oracle import ref_loader
+        return ref_loader.available()
+    except Exception:
+        return False
+
+
+def cpu_baseline(name="c2", budget=12.0, min_tr=1, max_tr=10 ** 9, warm=0, cores=None, impl="port"):
+    """Gradient evals/sec of the reference algorithm with every host core busy on its own chain: the sum over cores of
+    (evaluations / busy seconds).  impl = "port": the numpy restatement (oracle/); "reference": the reference's own
+    WALNUTS.py + adaptiveIntegrators.py under the Philox shim (WALNUTSpy-mode workloads, when staged)."""
     cores = cores or os.cpu_count() or 1
     t0 = time.perf_counter()
-    res = _pool(cores).map(_cpu_worker, [(name, c, budget, min_tr, max_tr, warm) for c in range(cores)])
+    res = _pool(cores).map(_cpu_worker, [(name, c, budget, min_tr, max_tr, warm, impl) for c in range(cores)])
     wall = time.perf_counter() - t0
     rate = sum(r[0] / r[1] for r in res)
     n_tr = [r[2] for r in res]
-    return {"value": rate, "unit": "grad_evals/s", "cores": cores, "kind": "port",
+    return {"value": rate, "unit": "grad_evals/s", "cores": cores, "kind": impl,
             "sample": f"{cores} chains (one per process, OMP_NUM_THREADS=1) x {min(n_tr)}..{max(n_tr)} transitions of "
-                      f"{WORKLOADS[name]['workload']} on the numpy restatement of the reference "
+                      f"{WORKLOADS[name]['workload']} on "
+                      f"{'the numpy restatement of the reference' if impl == 'port' else 'the reference itself (WALNUTS.py, adaptiveIntegrators.py; Philox shim)'} "
                       f"({sum(r[0] for r in res):.0f} evals, {max(r[1] for r in res):.1f}s busy, wall {wall:.1f}s)",
             "per_core": rate / cores, "transitions_min": min(n_tr), "seconds": float(np.mean([r[1] for r in res])),
             "seconds_per_transition": float(np.mean([r[1] / r[2] for r in res]))}
@@ -440,31 +458,30 @@ def gpu_leg(env, name, steps, warmup, chains=None, e2e=True, fp64_peak=None, kee
 
 def ess_leg(env, chains=ESS_CHAINS, n_draws=ESS_DRAWS):
     """min-ESS/sec: `chains` chains per GPU x `n_draws` transitions of the headline workload in ONE launch; bulk ESS
-    (rank-normalised, split chains) and split-R-hat over ALL chains of all GPUs after one all-gather of the
-    monitored draws."""
-    from walnuts_b200 import diagnostics
+    (rank-normalised, split chains) and split-R-hat over ALL chains of all GPUs, computed by the library on the device
+    (wn_ess_rhat: one NCCL all-gather of the monitored draws, then sort / autocovariance kernels)."""
+    from walnuts_b200 import comm_unique_id
     torch = env.torch
     spec = WORKLOADS["c2"]
     q0, data = make_inputs(spec, chains, env.rank)
     cb = make_batch(spec, chains, (1 << 24) + env.rank * chains, env.local_rank, data, q0)
+    if env.world > 1:
+        box = [comm_unique_id() if env.rank == 0 else None]
+        env.dist.broadcast_object_list(box, src=0)            # 128 bytes of rendezvous, not data
+        cb.comm_init_rank(env.world, env.rank, box[0])
     draws = torch.empty((n_draws, chains, MONITOR), dtype=torch.float64, device=env.dev)
     env.barrier()
     cb.run_device(n_draws, draws=draws)
     ms = cb.last_kernel_ms()
     f, b = cb.last_grad_evals()
-    cb.close()
     env.barrier()
     (ms_max,), (evals_all,) = env.reduce([ms], [float(f + b)])
-    if env.world > 1:
-        parts = [torch.empty_like(draws) for _ in range(env.world)]
-        env.dist.all_gather(parts, draws)                      # the one collective: monitored draws over NVLink
-        draws = torch.cat(parts, 1)
-    per, rh, half = [], [], []
-    if env.rank == 0:
-        for j in range(MONITOR):
-            e, r = diagnostics.ess_bulk(draws[:, :, j].t().contiguous())
-            per.append(float(e)); rh.append(float(r))
-            half.append(float(diagnostics.ess_bulk(draws[:n_draws // 2, :, j].t().contiguous())[0]))
+    t0 = time.perf_counter()
+    per, rh = cb.ess_rhat(draws)
+    stat_s = time.perf_counter() - t0
+    half, _ = cb.ess_rhat(draws[:n_draws // 2])
+    cb.close()
+    per, rh, half = [float(x) for x in per], [float(x) for x in rh], [float(x) for x in half]
     sig = sigma_vec()[:MONITOR]
     if env.rank != 0:
         return None
@@ -476,9 +493,11 @@ def ess_leg(env, chains=ESS_CHAINS, n_draws=ESS_DRAWS):
             "tau_max_draws": total / per[k], "split_chain_length": n_draws // 2, "rhat_max": float(np.nanmax(rh)),
             "min_ess_first_half_of_draws": half[k],        # ESS must grow with the draws: ~ half of min_ess
             "ess_per_coordinate": per, "rhat_per_coordinate": rh, "sigma_monitored": [float(x) for x in sig],
+            "statistics_seconds": stat_s,
             "estimator": "bulk ESS: rank-normalised, split chains, Geyer initial monotone sequence on chain-averaged "
                          "autocorrelations with all lags available (Vehtari et al. 2021 = arviz.ess default, "
-                         "mainGaussESS.py:50-55); chains start from exact draws of the target"}
+                         "mainGaussESS.py:50-55), computed on the device by wn_ess_rhat over the chains of all GPUs "
+                         "(one NCCL all-gather); chains start from exact draws of the target"}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -487,7 +506,9 @@ def reference_arm(args):
     Every core advances its own chain: `warmup` untimed transitions (capped at 1), then timed transitions until the
     time budget is used (at least 4, at most --steps).  One step = one transition of every core's chain; `steps` is
     the number actually executed by every core."""
-    cb = cpu_baseline("c2", budget=args.ref_budget, min_tr=4, max_tr=max(4, args.steps), warm=min(1, args.warmup))
+    impl = "reference" if reference_available() else "port"
+    cb = cpu_baseline("c2", budget=args.ref_budget, min_tr=args.ref_min_transitions,
+                      max_tr=max(args.ref_min_transitions, args.steps), warm=min(1, args.warmup), impl=impl)
     try:
         extra_c = cpu_baseline_c(6.0)
     except Exception as e:
@@ -517,6 +538,7 @@ def main():
     ap.add_argument("--ess-chains", type=int, default=ESS_CHAINS)
     ap.add_argument("--ess-draws", type=int, default=ESS_DRAWS)
     ap.add_argument("--ref-budget", type=float, default=60.0, help="seconds per core of the reference arm")
+    ap.add_argument("--ref-min-transitions", type=int, default=4, help="timed transitions per core of the reference arm")
     args = ap.parse_args()
 
     if args.impl == "reference":

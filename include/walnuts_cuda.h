@@ -48,6 +48,7 @@ extern "C" {
 #define WN_TARGET_STOCK_WATSON 4 /* WALNUTSpy_examples/StockWatson/sw_innov.stan; key "y" [T] */
 #define WN_TARGET_CORR_GAUSS 5   /* targetDistr.corrGauss :25-31 (2-d, rho = 0.5)             */
 #define WN_TARGET_FUNNEL_PKG 6   /* test/targets.py:23-29 (different density from funnel10)   */
+#define WN_TARGET_DENSE_GAUSS 7  /* lp = -1/2 q^T P q, dense precision P; data key "precision" [d*d]; d <= 128 */
 
 /* User-defined CUDA targets (the role of the reference's arbitrary Python lpFun / logp, grad callables and of
  * walnuts_stan.py's compiled model): ids returned by wn_register_user_target() start here. */
@@ -100,7 +101,7 @@ typedef struct wn_config {
 int wn_abi_version(void);
 
 /* name -> WN_TARGET_* ("std_normal","diag_gauss","funnel","logreg","stock_watson",
- * "corr_gauss","funnel_pkg"); <0 if unknown. */
+ * "corr_gauss","funnel_pkg","dense_gauss"); <0 if unknown. */
 int wn_target_id(const char* name);
 
 /* Load a user-target plug-in (built by walnuts_b200.targets.cuda_target() from csrc/wn_user_api.cuh, the user's
@@ -113,7 +114,7 @@ int wn_create(const wn_config* cfg, wn_handle** out);
 void wn_destroy(wn_handle* h);
 
 /* Target data / per-chain tuning.  `key`: "inv_var" [d], "inv_mass" [d] (PACKAGE mode metric,
- * walnuts.py:298), "X" [N*P row-major], "y" [N or T], "tau" [1], "H" [n_chains] and "delta"
+ * walnuts.py:298), "X" [N*P row-major], "y" [N or T], "tau" [1], "precision" [d*d row-major], "H" [n_chains] and "delta"
  * [n_chains] (per-chain macro step / tolerance, overriding cfg.H0 / cfg.delta).
  * `on_device` != 0: `ptr` is a device pointer on cfg.device. */
 int wn_set_data(wn_handle* h, const char* key, const double* ptr, int64_t n, int on_device);

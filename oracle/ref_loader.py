@@ -1,8 +1,9 @@
 """Load the REAL reference (when /root/reference is present) and run it under an injected RNG.
 
-TEST INFRASTRUCTURE ONLY; used by tests/golden/make_golden.py to generate the committed
-fixtures and by tests/test_oracle_vs_reference.py to pin the restatements in oracle/.
-Nothing here may be used at run time on the GPU box (it has no /root/reference).
+TEST / BASELINE INFRASTRUCTURE ONLY; used by tests/golden/make_golden.py to generate the committed fixtures, by
+tests/test_oracle_golden.py to pin the restatements in oracle/ against the live reference, and by
+`bench.py --impl reference` (the CPU arm) through the copy staged in oracle/_ref by oracle/stage_ref.py.  The product
+(walnuts_b200/) never imports it.
 
 Recipe: SURVEY.md appendix C.  The package `walnuts/__init__.py` imports bridgestan (absent),
 so walnuts/walnuts.py is loaded by path; WALNUTSpy/WALNUTS.py imports an unused matplotlib,
@@ -18,7 +19,18 @@ import numpy as np
 
 from . import philox
 
-REF_ROOT = os.environ.get("WALNUTS_REFERENCE", "/root/reference")
+def _ref_root():
+    """$WALNUTS_REFERENCE, else /root/reference (the build container), else the copy staged by oracle/stage_ref.py
+    (oracle/_ref: the only form in which the reference reaches the GPU box)."""
+    env = os.environ.get("WALNUTS_REFERENCE")
+    if env:
+        return env
+    if os.path.isfile("/root/reference/WALNUTSpy/WALNUTS.py"):
+        return "/root/reference"
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+REF_ROOT = _ref_root()
 
 
 def available():
@@ -102,7 +114,7 @@ def philox_numpy_random(seed, chain, M, first_iteration=1):
 
 def run_walnutspy(lpFun, q0, integrator_name, H0, delta0, numIter, M, minC=0, maxC=10,
                   seed=0, chain=0, stepSizeRandScale=0.2, use_philox=True, np_seed=None,
-                  generated=None, warmupIter=0, recordOrbitStats=False):
+                  generated=None, warmupIter=0, recordOrbitStats=False, first_iteration=1):
     """Run the real WALNUTS.WALNUTS; adaptation off (fixed H, delta) unless warmupIter > 0, which switches on the
     reference's default warm-up adaptation (adaptH, adaptDelta with their default targets, WALNUTS.py:111-129)."""
     wn, ai, _ = load_walnutspy()
@@ -117,7 +129,7 @@ def run_walnutspy(lpFun, q0, integrator_name, H0, delta0, numIter, M, minC=0, ma
         kw["recordOrbitStats"] = True      # returns (samples, diagnostics, orbitMin, orbitMax), WALNUTS.py:724-725
     with np.errstate(all="ignore"), contextlib.redirect_stdout(open(os.devnull, "w")):
         if use_philox:
-            with philox_numpy_random(seed, chain, M):
+            with philox_numpy_random(seed, chain, M, first_iteration):
                 return wn.WALNUTS(lpFun, **kw)
         np.random.seed(np_seed)
         return wn.WALNUTS(lpFun, **kw)

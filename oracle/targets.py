@@ -44,6 +44,17 @@ def make_diag_gauss(sigma):
     return diag_gauss
 
 
+def make_dense_gauss(precision):
+    """Dense-precision Gaussian (north_star; not in the reference): lp = -1/2 q^T P q, grad = -P q."""
+    P = np.ascontiguousarray(precision, dtype=np.float64)
+
+    def dense_gauss(q, hessian=False):
+        Pq = P @ q
+        return [-0.5 * float(q @ Pq), -Pq]
+
+    return dense_gauss
+
+
 def corr_gauss(q, hessian=False):
     """targetDistr.corrGauss (targetDistr.py:25-31), rho = 0.5."""
     rho = 0.5

@@ -53,6 +53,8 @@ def oracle_target(name, d, data=None):
         return otargets.corr_gauss
     if name == "logreg":
         return otargets.make_logreg(data["X"], data["y"], float(np.asarray(data.get("tau", 1.0)).ravel()[0]))
+    if name == "dense_gauss":
+        return otargets.make_dense_gauss(data["precision"])
     if name == "stock_watson":
         return otargets.make_stock_watson(data["y"])
     raise KeyError(name)

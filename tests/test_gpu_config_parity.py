@@ -99,3 +99,55 @@ def test_c2_long_run_100_transitions_moments(cuda_lib, compat):
     fast = sigma < 1.0
     corr = np.mean(z[:, fast] * (q0 / sigma)[:, fast], axis=0)
     assert np.abs(corr).max() < 0.1
+
+
+def _random_precision(d, seed, cond=50.0):
+    rng = np.random.default_rng(seed)
+    Qm, _ = np.linalg.qr(rng.standard_normal((d, d)))
+    ev = np.exp(rng.uniform(-0.5 * np.log(cond), 0.5 * np.log(cond), d))
+    P = (Qm * ev) @ Qm.T
+    return 0.5 * (P + P.T)
+
+
+@pytest.mark.parametrize("integrator,d", [("R2P", 100), ("fixed", 100), ("D", 24), ("R2P", 7), ("R2P", 104), ("fixed", 33),
+                                          ("R2P", 120)])
+def test_dense_gauss_tensor_core_target(cuda_lib, integrator, d):
+    """Dense-precision Gaussian (north_star): gradient -P Q of the 8 lock-stepped chains of a CTA on the FP64 tensor
+    cores (DMMA, TMA-staged rows of P) for d <= 104, per-warp FMA version beyond (d = 120); odd d exercises the
+    non-bulk-copy tiles.  Oracle = numpy formula on the same streams (target not in the reference: parity unpinned
+    for the FUNCTION, the transition kernel is the pinned one)."""
+    P = _random_precision(d, seed=d)
+    cov = np.linalg.inv(P)
+    L = np.linalg.cholesky(cov)
+    q0 = np.random.default_rng(2).standard_normal((11, d)) @ L.T           # more chains than one CTA holds
+    H0 = (0.9 if integrator != "fixed" else 0.35) * np.sqrt(1.0 / np.linalg.eigvalsh(P).max())
+    dg = check("dense_gauss", q0, integrator, H0=H0, delta=0.3, M=6, n_iter=12, data={"precision": P},
+               chains=[0, 7, 8, 10], float_rtol=1e-7)
+    assert len(np.unique(dg[..., 19])) >= 1
+
+
+def test_dense_gauss_package_mode_and_moments(cuda_lib):
+    """The per-warp version behind walnuts(...) (package semantics) and a long-run moment check of the tensor-core
+    version: 4096 chains from exact draws keep the covariance P^-1."""
+    import walnuts_b200 as wb
+    from oracle import package_oracle as po
+    from oracle import targets as ot
+    d = 12
+    P = _random_precision(d, seed=3, cond=10.0)
+    tg = wb.targets.dense_gauss(P)
+    th0 = 0.3 * np.random.default_rng(1).standard_normal((3, d))
+    draws = wb.walnuts(None, th0, tg, tg, np.ones(d), 0.6, 6, 0.2, 0, 10, seed=5)
+    lp = ot.make_dense_gauss(P)
+    for c in range(3):
+        ref = po.walnuts(5, c, th0[c], lambda q: lp(q)[0], lambda q: lp(q)[1], np.ones(d), 0.6, 6, 0.2, 0, 10)
+        ok, err = close(draws[c], ref)
+        assert ok, err
+    n = 4096
+    cov = np.linalg.inv(P)
+    q0 = np.random.default_rng(4).standard_normal((n, d)) @ np.linalg.cholesky(cov).T
+    s, dgn = wb.WALNUTS(tg, q0, integrator=wb.adaptLeapFrogR2P, H0=0.5, delta0=0.3, numIter=30, warmupIter=0, M=7,
+                        adaptH=False, adaptDelta=False, seed=9, compat=False)
+    x = s[:, :, -1]
+    emp = np.cov(x.T)
+    se = np.sqrt((np.outer(np.diag(cov), np.diag(cov)) + cov ** 2) / n)      # SE of a Gaussian sample covariance
+    assert np.abs((emp - cov) / se).max() < 5.0

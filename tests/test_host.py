@@ -43,7 +43,9 @@ def test_python_callables_are_rejected_loudly(cuda_lib):
     with pytest.raises(TypeError):
         wb.targets.stdGauss(np.zeros(3))
     with pytest.raises(NotImplementedError):
-        wb.WALNUTS(wb.targets.stdGauss, np.zeros(3), generated=lambda q: q[:1], numIter=1, warmupIter=0, recordOrbitStats=True)
+        # orbit statistics of a `generated` that is not a selection of coordinates (index selections are supported)
+        wb.WALNUTS(wb.targets.stdGauss, np.zeros(3), generated=lambda q: 2.0 * q[:1], numIter=1, warmupIter=0,
+                   recordOrbitStats=True)
 
 
 def test_user_target_plugin_builds_and_registers(cuda_lib):
@@ -117,13 +119,15 @@ def test_bench_reference_arm_contract():
     import subprocess
     import sys
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
-                        "--warmup", "0"], capture_output=True, text=True, timeout=600)
+                        "--warmup", "0", "--ref-budget", "1", "--ref-min-transitions", "1"], capture_output=True,
+                       text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["metric"] == "grad_evals_per_sec" and line["unit"] == "grad_evals/s"
     assert line["higher_is_better"] is True and line["value"] > 0 and line["ms_per_step"] > 0
     assert line["config"]["workload"].startswith("diag_gauss_d1000")
     cb = line["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "sample" in cb
+    # "reference": the real WALNUTS.py is importable here (build container / staged copy); "port": the numpy restatement
+    assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] == line["value"] and "sample" in cb
     assert line["e2e"] == {"value": line["value"], "unit": "grad_evals/s", "h2d_bytes_per_step": 0,
                            "d2h_bytes_per_step": 0}

@@ -5,7 +5,7 @@ import os
 from . import build as _build
 
 TARGETS = {"std_normal": 0, "diag_gauss": 1, "funnel": 2, "logreg": 3, "stock_watson": 4,
-           "corr_gauss": 5, "funnel_pkg": 6}
+           "corr_gauss": 5, "funnel_pkg": 6, "dense_gauss": 7}
 MODE_WALNUTSPY, MODE_PACKAGE = 0, 1
 INT_FIXED, INT_D, INT_R2P = 0, 1, 2
 DIAG_COLS = 24

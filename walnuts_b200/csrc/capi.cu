@@ -140,7 +140,7 @@ int wn_target_id(const char* name) {
       {"std_normal", WN_TARGET_STD_NORMAL}, {"diag_gauss", WN_TARGET_DIAG_GAUSS},
       {"funnel", WN_TARGET_FUNNEL},         {"logreg", WN_TARGET_LOGREG},
       {"stock_watson", WN_TARGET_STOCK_WATSON}, {"corr_gauss", WN_TARGET_CORR_GAUSS},
-      {"funnel_pkg", WN_TARGET_FUNNEL_PKG}};
+      {"funnel_pkg", WN_TARGET_FUNNEL_PKG}, {"dense_gauss", WN_TARGET_DENSE_GAUSS}};
   for (auto& e : tab)
     if (!strcmp(e.n, name)) return e.id;
   return WN_EINVAL;
@@ -222,7 +222,11 @@ int wn_set_data(wn_handle* h, const char* key, const double* ptr, int64_t n, int
     std::vector<double> tmp((size_t)n);
     CUDA_TRY(h, cudaMemcpy(tmp.data(), h->d_p0, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
     h->inv_var_max = 0.0;
-    for (double x : tmp) h->inv_var_max = (fabs(x) > h->inv_var_max || x != x) ? fabs(x) : h->inv_var_max;
+    h->inv_var_min = tmp.empty() ? 0.0 : tmp[0];
+    for (double x : tmp) {
+      h->inv_var_max = (fabs(x) > h->inv_var_max || x != x) ? fabs(x) : h->inv_var_max;
+      h->inv_var_min = (x < h->inv_var_min || x != x) ? x : h->inv_var_min;     // NaN sticks: no certificate
+    }
     return WN_OK;
   }
   if (!strcmp(key, "inv_mass")) {
@@ -253,6 +257,12 @@ int wn_set_data(wn_handle* h, const char* key, const double* ptr, int64_t n, int
     if (c.target == WN_TARGET_STOCK_WATSON) { h->n_p0 = n; return upload(h, &h->d_p0, ptr, n, on_device); }
     h->n_p1 = n;
     return upload(h, &h->d_p1, ptr, n, on_device);
+  }
+  if (!strcmp(key, "precision")) {
+    if (c.target != WN_TARGET_DENSE_GAUSS) return fail(h, WN_EINVAL, "data key \"precision\" belongs to dense_gauss");
+    if (n != (int64_t)c.d * c.d) return fail(h, WN_EINVAL, "precision must have d*d entries (row-major [d, d])");
+    h->n_p0 = c.d;
+    return upload(h, &h->d_p0, ptr, n, on_device);
   }
   if (!strcmp(key, "data")) {   // user targets: the array handed to the user's lp_grad
     if (c.target < WN_TARGET_USER_BASE) return fail(h, WN_EINVAL, "data key \"data\" belongs to user targets");
@@ -361,6 +371,8 @@ static int run_async_impl(wn_handle* h, int64_t n_iter, double* d_draws, double*
     return fail(h, WN_ESTATE, "logreg needs data keys X [N*d] and y [N]");
   if (c.target == WN_TARGET_STOCK_WATSON && (!h->d_p0 || h->n_p0 * 3 != c.d))
     return fail(h, WN_ESTATE, "stock_watson needs data key y with T = d/3 entries");
+  if (c.target == WN_TARGET_DENSE_GAUSS && (!h->d_p0 || h->n_p0 != c.d))
+    return fail(h, WN_ESTATE, "dense_gauss needs data key precision [d*d]");
   if (c.mode == WN_MODE_PACKAGE && !h->d_inv_mass) return fail(h, WN_ESTATE, "package mode needs data key inv_mass");
   LaunchPlan p;
   const bool adapting = h->d_adapt_state != nullptr && h->iter_done < (uint32_t)h->warmup_iter;
@@ -396,6 +408,7 @@ static int run_async_impl(wn_handle* h, int64_t n_iter, double* d_draws, double*
   TargetParams tp;
   tp.p0 = h->d_p0; tp.p1 = h->d_p1; tp.p2 = h->d_p2; tp.n0 = (int)h->n_p0; tp.n1 = (int)h->n_p1;
   tp.c0 = (c.target == WN_TARGET_DIAG_GAUSS) ? h->inv_var_max : 1.0 / (h->tau * h->tau);
+  tp.c1 = (c.target == WN_TARGET_DIAG_GAUSS) ? h->inv_var_min : 0.0;
 
   if (h->d_adapt_state && !adapting && !h->adapt_exported) {
     // warm-up is over: freeze the adapted (H, delta) of every chain as its step size / tolerance

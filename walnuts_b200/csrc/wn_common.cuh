@@ -117,6 +117,43 @@ struct Group {
     }
   }
 
+  // Sum of FOUR doubles over a group of whole warps with a transposing butterfly: the first two exchange steps hand
+  // every lane ONE of the four values (6 instead of 20 64-bit shuffles and additions); lanes 0..3 of each warp then hold
+  // the warp totals, which are combined across warps in a fixed order through shared memory.
+  __device__ __forceinline__ static void sum4t(double (&x)[4], double* red, int& parity) {
+    static_assert(G >= 32, "sum4t: whole warps per chain");
+    const unsigned lane = threadIdx.x & 31u;
+    const bool b0 = lane & 1u, b1 = lane & 2u;
+    double k0 = b0 ? x[2] : x[0], k1 = b0 ? x[3] : x[1];
+    k0 += __shfl_xor_sync(0xffffffffu, b0 ? x[0] : x[2], 1);
+    k1 += __shfl_xor_sync(0xffffffffu, b0 ? x[1] : x[3], 1);
+    double k = b1 ? k1 : k0;
+    k += __shfl_xor_sync(0xffffffffu, b1 ? k0 : k1, 2);
+    k += __shfl_xor_sync(0xffffffffu, k, 4);
+    k += __shfl_xor_sync(0xffffffffu, k, 8);
+    k += __shfl_xor_sync(0xffffffffu, k, 16);
+    // lane l < 4 holds value 2 (l & 1) + (l >> 1)
+    if constexpr (G > 32) {
+      const int w = threadIdx.x >> 5;
+      double* buf = red + parity * (WARPS * 4);
+      if (lane < 4u) buf[w * 4 + 2 * (lane & 1u) + (lane >> 1)] = k;
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        double s = buf[i];
+#pragma unroll
+        for (int ww = 1; ww < WARPS; ++ww) s += buf[ww * 4 + i];
+        x[i] = s;
+      }
+      parity ^= 1;
+    } else {
+      x[0] = __shfl_sync(0xffffffffu, k, 0);
+      x[1] = __shfl_sync(0xffffffffu, k, 2);
+      x[2] = __shfl_sync(0xffffffffu, k, 1);
+      x[3] = __shfl_sync(0xffffffffu, k, 3);
+    }
+  }
+
   // sum of one double plus OR of a small flag word over the group: the flags ride on a warp-wide integer OR
   // (redux.sync, one instruction) and on the second slot of the shared exchange instead of a second shuffle tree
   __device__ __forceinline__ static void sum1_flags(double& x, unsigned& flags, double* red, int& parity) {

@@ -28,19 +28,19 @@ template <int G, int E2>
 using DiagT = DiagGaussT<G, E2, false>;
 
 template <template <int, int> class T, int G, int E2, int NT, int MINB = 1, bool ADAPT = false, bool EXT = false,
-          int KSET = KSET_ANY, bool CTLSM = false>
+          int KSET = KSET_ANY, bool CTLSM = false, int NSMV = 0>
 static LaunchPlan plan_wpy() {
   LaunchPlan p;
-  p.fn = (const void*)walnutspy_kernel<T, G, E2, NT, MINB, ADAPT, EXT, KSET, CTLSM>;
+  p.fn = (const void*)walnutspy_kernel<T, G, E2, NT, MINB, ADAPT, EXT, KSET, CTLSM, NSMV>;
   p.G = G; p.E2 = E2; p.NT = NT;
-  p.smem = (size_t)wpy_smem_doubles<T, G, E2, NT, ADAPT, KSET>() * sizeof(double);
+  p.smem = (size_t)wpy_smem_doubles<T, G, E2, NT, ADAPT, KSET, NSMV>() * sizeof(double);
   p.package = false;
   return p;
 }
 // plain family: the kernel set follows from the family (FAM_NUTS: fixedLeapFrog, FAM_WPY: D / R2P)
-template <int FAM, template <int, int> class T, int G, int E2, int NT, int MINB = 1, bool CTLSM = false>
+template <int FAM, template <int, int> class T, int G, int E2, int NT, int MINB = 1, bool CTLSM = false, int NSMV = 0>
 static LaunchPlan plan_plain() {
-  return plan_wpy<T, G, E2, NT, MINB, false, false, (FAM == FAM_NUTS) ? KSET_FIXED : KSET_ADAPT, CTLSM>();
+  return plan_wpy<T, G, E2, NT, MINB, false, false, (FAM == FAM_NUTS) ? KSET_FIXED : KSET_ADAPT, CTLSM, NSMV>();
 }
 template <template <int, int> class T, int G, int E2, int NT>
 static LaunchPlan plan_pkg() {
@@ -103,10 +103,31 @@ static bool pick_plan_family(const wn_config& c, LaunchPlan& p) {
             case 4: p = plan_plain<FAM, DiagT, 256, 2, 256, 4>(); return true;    // ... 32 warps / SM (64 registers)
             case 5: p = plan_plain<FAM, DiagT, 64, 8, 64, 6>(); return true;      // 2 warps per chain, 12 warps / SM
             case 6: p = plan_plain<FAM, DiagT, 128, 4, 128, 4>(); return true;
+            case 7: p = plan_plain<FAM, DiagT, 128, 4, 128, 5>(); return true;    // 5 blocks / SM (96 registers)
+            case 8: case 9: case 10:
+              // plain NUTS with ONE warp per chain (32 coordinates per lane, inverse variances in shared memory, gradient
+              // recomputed): no replicated scalar work, no block barriers
+              if constexpr (FAM == FAM_NUTS) {
+                const int var = atoi(v);
+                if (var == 8) p = plan_plain<FAM, DiagSmT, 32, 16, 64, 3, false, 2>();   // 6 chains / SM, two levels in smem
+                else if (var == 9) p = plan_plain<FAM, DiagSmT, 32, 16, 64, 4>();
+                else p = plan_plain<FAM, DiagSmT, 32, 16, 128, 2>();
+                return true;
+              }
+              break;
+            case 11: case 12:
+              if constexpr (FAM == FAM_NUTS) {
+                if (atoi(v) == 11) p = plan_plain<FAM, DiagT, 128, 4, 128, 3, false, 2>();
+                else p = plan_plain<FAM, DiagT, 128, 4, 128, 3, false, 3>();
+                return true;
+              }
+              break;
             default:
-              // D / R2P: 4 blocks / SM at 124 registers; plain NUTS (level loop): 3 blocks / SM at 168 registers
-              // measured 3.41e8 against 2.62e8 grad evals/s at 128 registers (spills)
-              if constexpr (FAM == FAM_NUTS) p = plan_plain<FAM, DiagT, 128, 4, 128, 3>();
+              // D / R2P: 128 threads x 8 coordinates, 4 blocks / SM at 124 registers.  Plain NUTS (level loop): ONE
+              // warp per chain, 32 coordinates per lane, inverse variances in shared memory, gradient recomputed
+              // (DiagSmT) -- no replicated scalar work, no block barrier per leaf pair: 4.05e8 grad evals/s against
+              // 3.5e8 for 4 warps per chain at 168 registers (WN_VARIANT=2 / 11 / 12) and 1.68e8 for the flat loop
+              if constexpr (FAM == FAM_NUTS) p = plan_plain<FAM, DiagSmT, 32, 16, 64, 4>();
               else p = plan_plain<FAM, DiagT, 128, 4, 128, 4>();
               return true;
           }
@@ -157,12 +178,32 @@ static bool pick_plan_family(const wn_config& c, LaunchPlan& p) {
       if (T <= 64 * 4) {
         // 6 blocks / SM (168 registers, 12 warps) measured 9 % faster than 4 blocks at 255 registers
         // (8 blocks / SM at 128 registers: spills, same throughput)
-        if constexpr (FAM == FAM_WPY || FAM == FAM_NUTS) p = plan_plain<FAM, StockWatsonT, 64, 7, 64, 6>();
+        if constexpr (FAM == FAM_WPY || FAM == FAM_NUTS) {
+          const char* v = getenv("WN_VARIANT");
+          if (v && atoi(v) == 1) p = plan_plain<FAM, StockWatsonT, 64, 7, 64, 5>();     // 5 blocks / SM, 200 registers
+          else p = plan_plain<FAM, StockWatsonT, 64, 7, 64, 6>();
+        }
         else p = plan_for<FAM, StockWatsonT, 64, 7, 64>();
         return true;
       }
       if (T <= 128 * 4) { p = plan_for<FAM, StockWatsonT, 128, 7, 128>(); return true; }
       return false;
+    }
+    case WN_TARGET_DENSE_GAUSS: {
+      if (c.d > 128) return false;
+      // plain WALNUTSpy kernels: the gradient of the CTA's 8 lock-stepped chains on the FP64 tensor cores (DMMA) with
+      // TMA-staged rows of P; everything else (package mode, warm-up adaptation, other integrators, d > 104) on the
+      // per-warp FMA version
+      if constexpr (FAM == FAM_WPY || FAM == FAM_NUTS) {
+        const char* v = getenv("WN_VARIANT");
+        if (!(v && atoi(v) == 1) && c.d <= 104) {
+          if (c.d <= 32) p = plan_plain<FAM, DenseGaussMma32T, 32, 2, 256>();
+          else p = plan_plain<FAM, DenseGaussMma104T, 32, 2, 256>();
+          return true;
+        }
+      }
+      p = plan_for<FAM, DenseGaussT, 32, 2, 256>();
+      return true;
     }
     case WN_TARGET_CORR_GAUSS:
       if (c.d != 2) return false;

@@ -32,7 +32,7 @@ struct wn_handle {
   double FPtol = 1.0e-8, gradThresh = 5.0;
   int64_t n_p0 = 0, n_p1 = 0;
   double tau = 1.0;
-  double inv_var_max = 1.0;
+  double inv_var_max = 1.0, inv_var_min = 1.0;
   uint32_t iter_done = 0, iter_base = 0;   // iter_base: iter_done at creation (cfg.first_iteration - 1)
   float last_ms = 0.f;
   int64_t last_launches = 0;

@@ -15,7 +15,8 @@ struct TargetParams {
   const double* p1;  // -                | y [N]             | -
   const double* p2;  // -                | X^T [P,N]         | -
   int n0, n1;        // -                | N, P              | T
-  double c0;         // -                | 1/tau^2           | -
+  double c0;         // max |inv_var|    | 1/tau^2           | -
+  double c1;         // min inv_var      | -                 | -
 };
 
 // coordinate index of element e (= 2*e2 + h) held by thread t
@@ -39,13 +40,17 @@ struct DiagGaussT {
   // coordinate; if the bound is ever violated the sampler re-runs the pass with per-step energies.
   static constexpr bool LAZY_ENERGY = true;
   static constexpr bool COOP = false;
+  // every thread's partial of H = 1/2 sum s q^2 + 1/2 sum v^2 is non-negative when all inverse variances are
+  // (nonneg_ok): a single partial that exceeds the start energy by delta certifies a failed search attempt
+  static constexpr bool NONNEG_ENERGY = true;
   __host__ __device__ static constexpr int smem_doubles(int) { return 0; }
   __device__ __forceinline__ int coord(int e, int t) const { return coord_of<G>(e, t); }
   double s[UNIT ? 1 : E];
   double smax;     // max inv_var over ALL coordinates (host-computed, TargetParams::c0)
-  bool lazy_ok;
+  bool lazy_ok, nonneg_ok;
   __device__ __forceinline__ void init(const TargetParams& tp, int d, int t, double*) {
     lazy_ok = true;
+    nonneg_ok = UNIT ? true : (tp.c1 >= 0.0);    // host-computed minimum of inv_var over ALL coordinates
     smax = UNIT ? 1.0 : tp.c0;
     lazy_ok = (smax <= 0x1p60);
     if constexpr (!UNIT) {
@@ -90,6 +95,73 @@ struct DiagGaussT {
       if constexpr (UNIT) g[e] = -q[e];
       else g[e] = -(q[e] * s[e]);
     }
+  }
+};
+
+// Diagonal Gaussian with the inverse variances in SHARED memory (one table per block) and a gradient that is
+// recomputed from q where it is needed (REGRAD): leaves the register file to q and v when ONE warp holds a whole
+// high-dimensional chain (plain NUTS at d = 1000: 32 coordinates per lane).
+template <int G, int E2>
+struct DiagSmT {
+  static constexpr int E = 2 * E2;
+  static constexpr bool PAIR_LAYOUT = true;
+  static constexpr bool BLOCK_LOCKSTEP = false;
+  static constexpr bool LAZY_ENERGY = false;
+  static constexpr bool COOP = false;
+  static constexpr bool REGRAD = true;
+  __host__ __device__ static constexpr int smem_doubles(int) { return 2 * G * E2; }
+  __device__ __forceinline__ int coord(int e, int t) const { return coord_of<G>(e, t); }
+  const double2* ssm;     // this lane's first pair; pair e2 at ssm[e2 * G]
+  __device__ __forceinline__ void init(const TargetParams& tp, int d, int t, double* tsm) {
+    for (int j = threadIdx.x; j < 2 * G * E2; j += blockDim.x) tsm[j] = (j < d) ? tp.p0[j] : 0.0;
+    __syncthreads();
+    ssm = reinterpret_cast<const double2*>(tsm) + t;
+  }
+  // One leapfrog step (reference adaptiveIntegrators.py:50-55) fused per coordinate, the gradient recomputed from q
+  // at both ends instead of being carried: the same operations in the same order as the generic micro_step on this
+  // layout (bit-identical), without a gradient array.  Returns this lane's partial of H = -lp + 1/2 sum v^2.
+  __device__ __forceinline__ double leapfrog_energy(double (&q)[E], double (&v)[E], double hh, double ha) const {
+    double lp0 = 0.0, lp1 = 0.0, ke0 = 0.0, ke1 = 0.0;
+#pragma unroll
+    for (int e2 = 0; e2 < E2; ++e2) {
+      const double2 sv = ssm[e2 * G];
+      double q0 = q[2 * e2], q1 = q[2 * e2 + 1], v0 = v[2 * e2], v1 = v[2 * e2 + 1];
+      v0 = fma(ha, -(q0 * sv.x), v0);
+      v1 = fma(ha, -(q1 * sv.y), v1);
+      q0 = fma(hh, v0, q0);
+      q1 = fma(hh, v1, q1);
+      const double g0 = -(q0 * sv.x), g1 = -(q1 * sv.y);
+      lp0 = fma(q0, g0, lp0);
+      lp1 = fma(q1, g1, lp1);
+      v0 = fma(ha, g0, v0);
+      v1 = fma(ha, g1, v1);
+      ke0 = fma(v0, v0, ke0);
+      ke1 = fma(v1, v1, ke1);
+      q[2 * e2] = q0; q[2 * e2 + 1] = q1; v[2 * e2] = v0; v[2 * e2 + 1] = v1;
+    }
+    return fma(0.5, ke0 + ke1, -(0.5 * (lp0 + lp1)));
+  }
+  __device__ __forceinline__ double lp_only(const double (&q)[E]) const {
+    double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+    for (int e2 = 0; e2 < E2; ++e2) {
+      const double2 sv = ssm[e2 * G];
+      acc0 = fma(q[2 * e2], -(q[2 * e2] * sv.x), acc0);
+      acc1 = fma(q[2 * e2 + 1], -(q[2 * e2 + 1] * sv.y), acc1);
+    }
+    return 0.5 * (acc0 + acc1);
+  }
+  __device__ __forceinline__ double lp_grad(const double (&q)[E], double (&g)[E], double*, int&) const {
+    double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+    for (int e2 = 0; e2 < E2; ++e2) {
+      const double2 sv = ssm[e2 * G];
+      g[2 * e2] = -(q[2 * e2] * sv.x);
+      g[2 * e2 + 1] = -(q[2 * e2 + 1] * sv.y);
+      acc0 = fma(q[2 * e2], g[2 * e2], acc0);
+      acc1 = fma(q[2 * e2 + 1], g[2 * e2 + 1], acc1);
+    }
+    return 0.5 * (acc0 + acc1);
   }
 };
 
@@ -317,7 +389,11 @@ struct StockWatsonT {
     double b1[3] = {q[0], q[B], q[3 * B]};      // thread 0's z1, x1, tS travel with the scan's exchange
     scan<2, true, 3>(ch, ex1, red, parity, b1);
     const double Z0 = b1[0], X0 = b1[1], tS = b1[2];
-    const double sigma = exp(-0.5 * tS), etS = exp(tS);
+    // sigma = exp(-tS / 2) and exp(tS) in ONE instruction stream: even lanes evaluate the first, odd lanes the second
+    // (same operation on the same operand as the sequential form: bit-identical)
+    const bool oddl = (threadIdx.x & 1) != 0;
+    const double e2v = exp(oddl ? tS : -0.5 * tS);
+    const double sigma = __shfl_sync(0xffffffffu, e2v, 0), etS = __shfl_sync(0xffffffffu, e2v, 1);
     double lp = 0.0;
     double ez[B], w[B], c[B], locC[B];
     double ch2[1] = {0.0}, ex2[1];
@@ -1067,5 +1143,205 @@ template <int G, int E2>
 using LogRegMma32T = LogRegMmaTP<G, E2, 32>;
 template <int G, int E2>
 using LogRegMma104T = LogRegMmaTP<G, E2, 104>;
+
+}  // namespace wn
+
+namespace wn {
+
+// ---- dense-precision Gaussian (north_star: "tensor cores only where the gradient really is a dense contraction across
+// lock-stepped chains"): lp = -1/2 q^T P q, grad = -P q with a dense symmetric positive-definite precision matrix P
+// [d, d] (row-major, data key "precision").  Not in the reference (its Gaussians are diagonal or 2-d: targetDistr.py:18-31).
+//
+// Per-warp version (G = 32): serves package mode, the warm-up adaptation and the extended integrators.  The chain's q is
+// published to the warp's shared row; lane t forms the rows of its own coordinates with FMAs, P read through L2.
+template <int G, int E2>
+struct DenseGaussT {
+  static constexpr int E = 2 * E2;
+  static constexpr bool PAIR_LAYOUT = true;
+  static constexpr bool BLOCK_LOCKSTEP = true;     // the block's chains stream the same rows of P: keep them in step
+  static constexpr bool LAZY_ENERGY = false;
+  static constexpr bool COOP = false;
+  static constexpr int PMAX = 2 * G * E2;
+  static_assert(G == 32, "dense Gaussian target: one warp per chain");
+  __host__ __device__ static constexpr int smem_doubles(int NT) { return (NT / 32) * PMAX; }
+  const double* Pm;
+  int d_;
+  double* qs;
+  __device__ __forceinline__ int coord(int e, int t) const { return coord_of<G>(e, t); }
+  __device__ __forceinline__ void init(const TargetParams& tp, int d, int, double* tsm) {
+    Pm = tp.p0; d_ = d;
+    qs = tsm + (threadIdx.x >> 5) * PMAX;
+  }
+  __device__ __forceinline__ double lp_grad(const double (&q)[E], double (&g)[E], double*, int&) const {
+    const int t = threadIdx.x & 31;
+    __syncwarp();
+#pragma unroll
+    for (int e = 0; e < E; ++e) qs[coord_of<G>(e, t)] = q[e];
+    __syncwarp();
+    double lp = 0.0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int r = coord_of<G>(e, t);
+      double acc = 0.0;
+      if (r < d_) {
+        const double* row = Pm + (size_t)r * d_;
+        for (int k = 0; k < d_; ++k) acc = fma(__ldg(row + k), qs[k], acc);
+      }
+      g[e] = -acc;
+      lp = fma(q[e], acc, lp);
+    }
+    return -0.5 * lp;
+  }
+};
+
+// Tensor-core version for the plain WALNUTSpy kernels: the 8 lock-stepped chains of a CTA are the N = 8 of
+// `mma.sync.m8n8k4.f64` (SASS DMMA.8x8x4), exactly as in LogRegMmaTP: G[d x 8 chains] = P[d x d] Q[d x 8].  P streams in
+// tiles of 8 rows (8 d doubles, contiguous) through per-warp 3-stage rings filled by bulk async copies (TMA engine,
+// SASS UBLKCP) on per-stage mbarriers; Q lives in registers as B fragments for the whole evaluation; the C fragment of a
+// tile IS the gradient of its 8 coordinates for the 8 chains, and q . (P q) accumulates the log density on the way.
+template <int G, int E2, int PCAP>
+struct DenseGaussMmaTP {
+  static constexpr int E = 2 * E2;
+  static constexpr bool PAIR_LAYOUT = true;
+  static constexpr bool BLOCK_LOCKSTEP = false;
+  static constexpr bool LAZY_ENERGY = false;
+  static constexpr bool COOP = true;
+  static constexpr int NTC = 256, NW = 8, C = 8, PMAX = 128, KS = PCAP / 4, RT = 8, S = 3;
+  static constexpr int WSTAGE = S * RT * PCAP;
+  static_assert(G == 32 && E2 == 2 && PCAP % 8 == 0 && PCAP <= 104, "tensor-core dense Gaussian: one warp per chain, d <= 104");
+  // shared: bs[PMAX][C] | gs[C][PMAX] | lps[NW][C] | act[C] | full[NW][4] | ring[NW][WSTAGE]
+  __host__ __device__ static constexpr int smem_doubles(int) { return PMAX * C + C * PMAX + NW * C + C + NW * 4 + NW * WSTAGE; }
+  const double* Pm;
+  int P;
+  double *bs, *gs, *lps, *act, *ring;
+  uint64_t* full;
+  __device__ __forceinline__ int coord(int e, int t) const { return coord_of<G>(e, t); }
+  __device__ __forceinline__ void init(const TargetParams& tp, int d, int, double* tsm) {
+    Pm = tp.p0; P = d;
+    bs = tsm; gs = bs + PMAX * C; lps = gs + C * PMAX; act = lps + NW * C;
+    full = reinterpret_cast<uint64_t*>(act + C);
+    ring = act + C + NW * 4;
+    for (int i = threadIdx.x; i < PMAX * C; i += NTC) { bs[i] = 0.0; gs[i] = 0.0; }
+    for (int i = threadIdx.x; i < NW * WSTAGE; i += NTC) ring[i] = 0.0;      // stale reads must be finite
+    if (threadIdx.x == 0) {
+      for (int i = 0; i < NW * 4; ++i) mbar_init(&full[i], 1);
+      mbar_fence_init();
+    }
+    __syncthreads();
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __device__ __forceinline__ double lp_grad(const double (&)[E], double (&)[E], double*, int&) const { return 0.0; }
+
+  __device__ __forceinline__ void publish(const double (&q)[E], bool active, bool) const {
+    const int w = threadIdx.x >> 5, t = threadIdx.x & 31;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int k = coord_of<G>(e, t);
+      if (k < P) bs[k * C + w] = active ? q[e] : 0.0;
+    }
+    if (t == 0) act[w] = active ? 1.0 : 0.0;
+  }
+
+  __device__ __forceinline__ static void dmma(double (&c)[2], double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+  }
+
+  // `gt`: tiles consumed so far by this warp modulo 2 S (stage g % S, mbarrier phase (g / S) & 1), kept by the caller
+  __device__ __forceinline__ void coop_eval(uint32_t& gt) const {
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    const int lr = lane >> 2, lc = lane & 3;
+    bool any = false;
+#pragma unroll
+    for (int c = 0; c < C; ++c) any = any || (act[c] != 0.0);
+    if (!any) return;
+    double bf[KS];                                   // Q as B fragments: B[k = 4 kk + lc][n = chain lr]
+#pragma unroll
+    for (int kk = 0; kk < KS; ++kk) bf[kk] = bs[(4 * kk + lc) * C + lr];
+    double lp0 = 0.0, lp1 = 0.0;
+    const int ntile = (P + RT - 1) / RT;
+    const int mine = (ntile > w) ? (ntile - w + NW - 1) / NW : 0;
+    const int stage_d = RT * P;
+    double* myring = ring + w * WSTAGE;
+    uint64_t* mybar = full + w * 4;
+    auto issue = [&](int j) {
+      const uint32_t g = gt + (uint32_t)j;
+      const int st_ = (int)(g % (uint32_t)S);
+      const int n0 = (w + j * NW) * RT;
+      const int nrows = min(RT, P - n0);
+      const uint32_t bytes = (uint32_t)(nrows * P * 8);
+      if ((bytes & 15u) == 0u && ((((size_t)n0 * P) & 1u) == 0u)) {
+        mbar_expect_tx(&mybar[st_], bytes);
+        bulk_g2s(myring + st_ * stage_d, Pm + (size_t)n0 * P, bytes, &mybar[st_]);
+      } else {       // odd d: a tile is not 16-byte aligned / sized -- plain copy, then complete the phase
+        for (int i = 0; i < nrows * P; ++i) myring[st_ * stage_d + i] = __ldg(Pm + (size_t)n0 * P + i);
+        mbar_arrive(&mybar[st_]);
+      }
+    };
+    if (lane == 0) {
+      if (mine > 0) issue(0);
+      if (mine > 1) issue(1);
+    }
+    for (int jj = 0; jj < mine; ++jj) {
+      const uint32_t g = gt + (uint32_t)jj;
+      const double* sx = myring + (g % (uint32_t)S) * stage_d;
+      const int n0 = (w + jj * NW) * RT;
+      const int nrows = min(RT, P - n0);
+      mbar_wait(&mybar[g % (uint32_t)S], (g / (uint32_t)S) & 1u);
+      double e4[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+      const double* ar = sx + lr * P + lc;
+      const bool rowok = lr < nrows;
+#pragma unroll
+      for (int kk = 0; kk < KS; ++kk) {
+        const double a = (rowok && 4 * kk + lc < P) ? ar[4 * kk] : 0.0;
+        dmma(e4[kk & 3], a, bf[kk]);
+      }
+      const double r0 = (e4[0][0] + e4[1][0]) + (e4[2][0] + e4[3][0]);     // (P q)[row n0 + lr][chain 2 lc]
+      const double r1 = (e4[0][1] + e4[1][1]) + (e4[2][1] + e4[3][1]);     //                   [chain 2 lc + 1]
+      if (rowok) {
+        const int row = n0 + lr;
+        gs[(2 * lc) * PMAX + row] = -r0;
+        gs[(2 * lc + 1) * PMAX + row] = -r1;
+        lp0 = fma(bs[row * C + 2 * lc], r0, lp0);
+        lp1 = fma(bs[row * C + 2 * lc + 1], r1, lp1);
+      }
+      __syncwarp();      // every lane is done with this stage before lane 0 refills it
+      if (lane == 0 && jj + 2 < mine) issue(jj + 2);
+    }
+    gt = (gt + (uint32_t)mine) % (uint32_t)(2 * S);
+    {
+      double v0 = lp0, v1 = lp1;
+#pragma unroll
+      for (int off = 16; off >= 4; off >>= 1) {
+        v0 += __shfl_xor_sync(0xffffffffu, v0, off);
+        v1 += __shfl_xor_sync(0xffffffffu, v1, off);
+      }
+      if (lr == 0) { lps[w * C + 2 * lc] = v0; lps[w * C + 2 * lc + 1] = v1; }
+    }
+    __syncthreads();
+    // the rings are rewritten by bulk copies (async proxy) in the next evaluation
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+
+  __device__ __forceinline__ double collect(const double (&)[E], double (&g)[E]) const {
+    const int w = threadIdx.x >> 5, t = threadIdx.x & 31;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int k = coord_of<G>(e, t);
+      g[e] = (k < P) ? gs[w * PMAX + k] : 0.0;
+    }
+    double lp = 0.0;
+    if (t == 0) {
+#pragma unroll
+      for (int ww = 0; ww < NW; ++ww) lp += lps[ww * C + w];
+      lp *= -0.5;
+    }
+    return lp;
+  }
+};
+template <int G, int E2>
+using DenseGaussMma32T = DenseGaussMmaTP<G, E2, 32>;
+template <int G, int E2>
+using DenseGaussMma104T = DenseGaussMmaTP<G, E2, 104>;
 
 }  // namespace wn

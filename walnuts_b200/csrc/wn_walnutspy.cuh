@@ -101,26 +101,44 @@ enum { KSET_ANY = 0, KSET_FIXED = 1, KSET_ADAPT = 2 };
 // left-end stack levels of the plain-NUTS level loop that live in shared memory (levels 1..NSM; deeper ones in L2 scratch)
 template <int G, int E2, int NT>
 struct NutsCfg {
-  static constexpr int NSM = 2;
+  // one level costs 2 * 2 E2 * NT doubles per block: 16 KB for the d = 1000 shape with 128 threads x 8 coordinates;
+  // measured there: 3 levels 3.53e8, 2 levels 3.45e8, 4 levels 3.15e8 grad evals/s (the L1 carve-out shrinks)
+  static constexpr int NSM = (G == 128 && E2 == 4) ? 3 : 2;
 };
+// one warp holds a whole d = 1000 chain (32 coordinates per lane): a level costs 16 KB per chain, one level fits
+template <int NT>
+struct NutsCfg<32, 16, NT> {
+  static constexpr int NSM = 1;
+};
+// targets whose per-thread energy partials are non-negative (pass-end failure certificate)
+template <class T, class = void>
+struct has_nonneg : std::false_type {};
+template <class T>
+struct has_nonneg<T, std::void_t<decltype(T::NONNEG_ENERGY)>> : std::bool_constant<T::NONNEG_ENERGY> {};
+// targets whose gradient is cheap to recompute from q (grad_only) need not keep g in registers between leaves
+template <class T, class = void>
+struct has_regrad : std::false_type {};
+template <class T>
+struct has_regrad<T, std::void_t<decltype(T::REGRAD)>> : std::bool_constant<T::REGRAD> {};
+
 template <class Target, int G, int ADAPT, int KSET>
 struct NutsFast {
   static constexpr bool value = (KSET == KSET_FIXED) && (G >= 32) && !Target::COOP && !Target::BLOCK_LOCKSTEP && !ADAPT;
 };
 // dynamic shared memory of walnutspy_kernel in doubles: checkpoint (or the plain-NUTS left-end slots + uniform buffer),
 // reduction scratch, target
-template <template <int, int> class TargetTT, int G, int E2, int NT, bool ADAPT, int KSET>
+template <template <int, int> class TargetTT, int G, int E2, int NT, bool ADAPT, int KSET, int NSMV = 0>
 __host__ __device__ constexpr int wpy_smem_doubles() {
   using Target = TargetTT<G, E2>;
   constexpr bool NF = NutsFast<Target, G, ADAPT, KSET>::value;
-  return (NF ? 2 * NutsCfg<G, E2, NT>::NSM : 3) * 2 * E2 * NT + (NF ? 2 * NT : 0) + 2 * ((G + 31) / 32) * 8 +
-         Target::smem_doubles(NT);
+  return (NF ? 2 * (NSMV ? NSMV : NutsCfg<G, E2, NT>::NSM) : 3) * 2 * E2 * NT + (NF ? 2 * NT : 0) +
+         2 * ((G + 31) / 32) * 8 + Target::smem_doubles(NT);
 }
 
 // CTLSM: the cold control block of chains that SHARE a warp (G < 32) lives in shared memory (one copy per chain)
 // instead of per-thread registers / local memory -- fewer registers, more resident warps (G >= 32 always does).
 template <template <int, int> class TargetTT, int G, int E2, int NT, int MINB = 1, bool ADAPT = false, bool EXT = false,
-          int KSET = KSET_ANY, bool CTLSM = false>
+          int KSET = KSET_ANY, bool CTLSM = false, int NSMV = 0>
 __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_constant__ RunParams P) {
   static_assert(!EXT || ADAPT, "EXT kernels are built with the adaptation code (inactive without wn_set_adapt)");
   static_assert(KSET == KSET_ANY || (!ADAPT && !EXT), "specialised kernel sets exist for the plain family only");
@@ -130,8 +148,9 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
   using Grp = Group<G>;
   using Target = TargetTT<G, E2>;
   constexpr bool NUTS_FAST = NutsFast<Target, G, ADAPT, KSET>::value;
-  constexpr int NSM = NutsCfg<G, E2, NT>::NSM;
+  constexpr int NSM = NSMV ? NSMV : NutsCfg<G, E2, NT>::NSM;   // NSMV: tuning override of the shared-memory levels
   constexpr bool LAZY = Target::LAZY_ENERGY && KSET != KSET_FIXED;   // plain NUTS consumes every step's energy
+  constexpr bool REGRAD = NUTS_FAST && has_regrad<Target>::value;      // g is recomputed, never carried
   // integrator predicates: compile-time where the kernel set fixes them
   auto is_fixed = [&]() -> bool { return KSET == KSET_FIXED || (KSET == KSET_ANY && P.kind == KIND_FIXED); };
   auto is_r2p = [&]() -> bool { return KSET != KSET_FIXED && P.kind == KIND_R2P; };
@@ -157,6 +176,7 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
   int parity = 0;
 
   // scratch addressing: vector vi, pair e2 -> scratch[((vi*E2 + e2) * nslot + slot) * G + t]
+  // (computed on demand: a hoisted base pointer + stride would cost four live registers in the hot loop)
   auto sc = [&](int vi, int e2) -> double2* {
     const size_t slot = (size_t)blockIdx.x * GPB + tid / G;
     return P.scratch + ((size_t)(vi * E2 + e2) * P.nslot + slot) * G + t;
@@ -533,9 +553,10 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
           for (int e2 = 0; e2 < E2; ++e2) *sc(pvec, e2) = *sc(V_STACK + 2 * lvl, e2);
         }
       };
-      // bookkeeping of one leaf with energy Hl and step h (WALNUTS.py:302-328 / :401-429 / :440-467 and the forward
-      // twins); returns false on a forced reject.  `pick` tells the caller to store the proposal.
-      auto leaf_book = [&](double Hl, double h, bool& pick) -> bool {
+      // bookkeeping of one leaf with energy Hl, step h and weight Wnew = exp(-Hl + H0) (lwtSum = 0 for fixedLeapFrog,
+      // WALNUTS.py:321-322,...; `ratio` = Wnew / (WnewSum + Wnew)): WALNUTS.py:302-328 / :401-429 / :440-467 and the
+      // forward twins; returns false on a forced reject.  `pick` tells the caller to store the proposal.
+      auto leaf_book = [&](double Hl, double h, double Wnew, double ratio, bool& pick) -> bool {
         ++nleaf;
         ++nF;
         mi += dstep;
@@ -549,14 +570,13 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
           if (level == 0 || (nleaf & 1u)) stop999 = 1;
           return false;
         }
-        const double Wnew = exp(-Hl + H0);                       // lwtSum = 0 for fixedLeapFrog (:321-322,...)
         if (level == 0) {
           WnewSum = Wnew;
           pick = true;                                           // :326,359
         } else {
           const double ws = WnewSum + Wnew;
           WnewSum = ws;
-          if (ws > WN_WT_SUM_THRESH) pick = ufetch(nseq++) < Wnew / ws;   // :426,464,512,554
+          if (ws > WN_WT_SUM_THRESH) pick = ufetch(nseq++) < ratio;   // :426,464,512,554
           orbitLen = orbitLen + h;                               // :432,...
         }
         if (pick) {
@@ -566,53 +586,69 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
         }
         return true;
       };
+      const bool odd_lane = (tid & 1) != 0;
+      // (one code instance each of the leapfrog step and of the dot products: the loops over the pair's two leaves and
+      //  over the spans are NOT unrolled -- with 32 coordinates per lane the pair body would otherwise outgrow the
+      //  instruction cache)
       do {
         const uint32_t nA = nleaf + 1u;
         const double hA = jitl(ufetch(nseq++));                  // :298 / :395 (two draws per leaf pair)
         double hB = 0.0;
         if (level == 0) orbitLen = orbitLen + hA;                // :300
         else hB = jitl(ufetch(nseq++));
-        hh = hA;
-        ha = 0.5 * hA;
-        micro_step();
-        double x[4] = {hp, 0.0, 0.0, 0.0};
-        int lvlA = 0;
-        if (level > 0) {
-          lvlA = (nA == 1u) ? level : (__ffs(nA - 1u) - 1);
-          put_left(lvlA);
-          hh = hB;
-          ha = 0.5 * hB;
-          micro_step();
-          x[1] = hp;
-          dots_left(lvlA, x[2], x[3]);
+        const int lvlA = (level == 0) ? 0 : ((nA == 1u) ? level : (__ffs(nA - 1u) - 1));
+        double x[4] = {0.0, 0.0, 0.0, 0.0};
+        const int nl = (level == 0) ? 1 : 2;
+#pragma unroll 1
+        for (int l = 0; l < nl; ++l) {
+          hh = l ? hB : hA;
+          ha = 0.5 * hh;
+          if constexpr (REGRAD) hp = target.leapfrog_energy(q, v, hh, ha); else micro_step();
+          if (l == 0) { x[0] = hp; if (level > 0) put_left(lvlA); }
+          else x[1] = hp;
         }
-        Grp::template sum<4>(x, red, parity);
-        bool pick;
-        if (!leaf_book(x[0], hA, pick)) { out = 1; break; }
-        if (pick) {
-          if (level == 0) {
+        // post-order sub-U-turn checks ending at the pair's second leaf (WALNUTS.py:22-41 plan; :479,568,582); the
+        // first one (the pair itself, span 2) shares its reduction with the two energies, and the leaves' bookkeeping
+        // follows it
+        bool sub = false;
+        int lvl = lvlA;
+#pragma unroll 1
+        for (int sp = 1;; ++sp) {
+          if (level > 0) dots_left(lvl, x[2], x[3]);
+          Grp::sum4t(x, red, parity);
+          if (sp == 1) {
+            // the two leaves' weights and selection ratios in ONE instruction stream: even lanes evaluate leaf A, odd
+            // lanes leaf B (same operations on the same operands as the sequential form: bit-identical)
+            const double Wl = exp(-(odd_lane ? x[1] : x[0]) + H0);
+            const double WA = __shfl_sync(0xffffffffu, Wl, 0), WB = __shfl_sync(0xffffffffu, Wl, 1);
+            const double ws1 = WnewSum + WA;
+            const double rl = (odd_lane ? WB : WA) / (odd_lane ? ws1 + WB : ws1);
+            const double rA = __shfl_sync(0xffffffffu, rl, 0), rB = __shfl_sync(0xffffffffu, rl, 1);
+            bool pick;
+            if (!leaf_book(x[0], hA, WA, rA, pick)) { out = 1; break; }
+            if (pick) {
+              if (level == 0) {
 #pragma unroll
-            for (int e2 = 0; e2 < E2; ++e2) *sc(pvec, e2) = make_double2(q[2 * e2], q[2 * e2 + 1]);
-          } else {
-            prop_from_left(lvlA);
+                for (int e2 = 0; e2 < E2; ++e2) *sc(pvec, e2) = make_double2(q[2 * e2], q[2 * e2 + 1]);
+              } else {
+                prop_from_left(lvlA);
+              }
+            }
+            if (level == 0) break;
+            if (!leaf_book(x[1], hB, WB, rB, pick)) { out = 1; break; }
+            if (pick) {
+#pragma unroll
+              for (int e2 = 0; e2 < E2; ++e2) *sc(pvec, e2) = make_double2(q[2 * e2], q[2 * e2 + 1]);
+            }
           }
+          sub = (x[2] < 0.0) || (xi * x[3] < 0.0);
+          if (sub || sp + 1 > level || (nleaf & ((1u << (sp + 1)) - 1u)) != 0u) break;
+          const uint32_t m = nleaf - (1u << (sp + 1)) + 1u;      // left end of the next larger span ending here
+          lvl = (m == 1u) ? level : (__ffs(m - 1u) - 1);
+          x[0] = 0.0;
+          x[1] = 0.0;
         }
-        if (level == 0) break;
-        if (!leaf_book(x[1], hB, pick)) { out = 1; break; }
-        if (pick) {
-#pragma unroll
-          for (int e2 = 0; e2 < E2; ++e2) *sc(pvec, e2) = make_double2(q[2 * e2], q[2 * e2 + 1]);
-        }
-        // post-order sub-U-turn checks ending at this leaf (WALNUTS.py:22-41 plan; :479,568,582)
-        bool sub = (x[2] < 0.0) || (xi * x[3] < 0.0);
-        for (int sp = 2; !sub && sp <= level && (nleaf & ((1u << sp) - 1u)) == 0u; ++sp) {
-          const uint32_t m = nleaf - (1u << sp) + 1u;
-          const int lvl = (m == 1u) ? level : (__ffs(m - 1u) - 1);
-          double y[2];
-          dots_left(lvl, y[0], y[1]);
-          Grp::template sum<2>(y, red, parity);
-          sub = (y[0] < 0.0) || (xi * y[1] < 0.0);
-        }
+        if (out) break;
         if (sub) { out = 2; break; }
       } while (nleaf < n_new);
       // ---- write the level's state back for the shared handlers (level end / iteration end) ----
@@ -763,6 +799,31 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
       if (st == ST_MACRO) nuts_level();
     }
     if (!NUTS_FAST && st == ST_PASS_END) do {  // a pass of 2^c micro-steps finished
+      if constexpr (has_nonneg<Target>::value && KSET == KSET_ADAPT && !ADAPT) {
+        // Local failure certificate of a search attempt (adaptiveIntegrators.py:87-92,129-132).  For targets whose
+        // energy partials are non-negative (-lp_t >= 0, kinetic part >= 0) the total satisfies Hend >= hp_t, also in
+        // floating point (adding non-negative terms never decreases a running sum, and fl(x - Href) is monotone in
+        // x).  So if ONE thread's partial alone is at least delta above the start energy, |Href - Hend| < delta is
+        // false whatever the other partials are -- the attempt has failed, with or without non-finite intermediate
+        // energies.  The unstable early attempts (c below the stability limit) end this way: one block-wide vote
+        // replaces the shuffle tree, the shared exchange and, when the magnitude bound tripped, the exact re-run.
+        if (rsearch && rc < rlim && target.nonneg_ok) {
+          const bool lf = (hp > rHref) && (fabs(rHref - hp) >= rdelta);
+          bool anyf;
+          if constexpr (G > 32) anyf = __syncthreads_or(lf) != 0;
+          else if constexpr (G > 1) anyf = __any_sync(Grp::mask(), lf) != 0;
+          else anyf = lf;
+          if (anyf) {
+            rEv += evmul << rc;
+            ++rc;
+            rexact = false;
+            load_ck(rsign);
+            start_pass(rc);
+            st = ST_RUN;
+            break;
+          }
+        }
+      }
       const bool unbounded = (smax & 0x7ff00000) >= LAZY_LIMIT ||
                              ((umax & 0x80000000u) && (int)(umax & 0x7ff00000u) >= LAZY_LIMIT);
       double Hend = hp;
@@ -1265,7 +1326,9 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
           st = ST_RUN;
           break;
         }
-        const double lpp = target.lp_grad(q, g, red, parity);        // :249
+        double lpp;
+        if constexpr (REGRAD) lpp = target.lp_only(q);               // the gradient is recomputed where it is used
+        else lpp = target.lp_grad(q, g, red, parity);                // :249
         x[0] = fma(0.5, ke, -lpp);
       }
       Grp::template sum<1>(x, red, parity);
@@ -1282,7 +1345,7 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
         const double2 qq = make_double2(q[2 * e2], q[2 * e2 + 1]);
         *sc(V_PARK_Q, e2) = qq;
         *sc(V_PARK_V, e2) = make_double2(v[2 * e2], v[2 * e2 + 1]);
-        *sc(V_PARK_G, e2) = make_double2(g[2 * e2], g[2 * e2 + 1]);
+        if constexpr (!REGRAD) *sc(V_PARK_G, e2) = make_double2(g[2 * e2], g[2 * e2 + 1]);
         *sc(V_PROP0, e2) = qq;
         if (P.orbit_min) { *sc(V_OMIN, e2) = qq; *sc(V_OMAX, e2) = qq; }   // :274-276
       }
@@ -1321,13 +1384,16 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
         const double xi = C.xi;
 #pragma unroll
         for (int e2 = 0; e2 < E2; ++e2) {
-          const double2 pq = *sc(V_PARK_Q, e2), pv = *sc(V_PARK_V, e2), pg = *sc(V_PARK_G, e2);
+          const double2 pq = *sc(V_PARK_Q, e2), pv = *sc(V_PARK_V, e2);
           *sc(V_PARK_Q, e2) = make_double2(q[2 * e2], q[2 * e2 + 1]);
           *sc(V_PARK_V, e2) = make_double2(xi * v[2 * e2], xi * v[2 * e2 + 1]);
-          *sc(V_PARK_G, e2) = make_double2(g[2 * e2], g[2 * e2 + 1]);
+          if constexpr (!REGRAD) {
+            const double2 pg = *sc(V_PARK_G, e2);
+            *sc(V_PARK_G, e2) = make_double2(g[2 * e2], g[2 * e2 + 1]);
+            g[2 * e2] = pg.x; g[2 * e2 + 1] = pg.y;
+          }
           q[2 * e2] = pq.x; q[2 * e2 + 1] = pq.y;
           v[2 * e2] = nxi * pv.x; v[2 * e2 + 1] = nxi * pv.y;
-          g[2 * e2] = pg.x; g[2 * e2 + 1] = pg.y;
         }
       }
       C.side = ns;

@@ -47,6 +47,18 @@ def ill_conditioned_gauss(d=1000, lo=-2.0, hi=2.0):
     return diag_gauss(np.logspace(lo, hi, d))
 
 
+def dense_gauss(precision):
+    """Zero-mean Gaussian with a dense symmetric positive-definite PRECISION matrix [d, d], d <= 128 (north_star: the
+    target whose gradient -P q is a dense contraction across lock-stepped chains; it runs on the FP64 tensor cores).
+    Not in the reference."""
+    P = np.ascontiguousarray(precision, dtype=np.float64)
+    if P.ndim != 2 or P.shape[0] != P.shape[1]:
+        raise ValueError("precision must be a square matrix")
+    if not np.allclose(P, P.T, rtol=1e-12, atol=0.0):
+        raise ValueError("precision must be symmetric")
+    return Target("dense_gauss", data={"precision": P}, d=P.shape[0], ref="north_star (not in the reference)")
+
+
 def stock_watson(y):
     """Stock-Watson stochastic-volatility model of the reference's example
     (WALNUTSpy_examples/StockWatson/sw_innov.stan:2-52, bridgestan default propto=True) on the
