@@ -5,11 +5,11 @@ Package protocol:   ``logp(theta) -> float``, ``grad(theta) -> (D,)`` (reference
 walnuts/walnuts.py:296-297, test/targets.py:4-29).
 
 Targets that exist in the reference are restated with the reference's own operation
-order; the three the reference lacks (diag Gaussian, logistic regression, Stock-Watson)
-are defined here and are the specification for the CUDA targets (SURVEY.md rows T2,T4,T5).
+order; the four the reference lacks (diag Gaussian, dense-precision Gaussian, logistic regression, Stock-Watson)
+are defined here and are the specification for the CUDA targets (SURVEY.md rows T2,T4,T5; north_star).
 
-PARITY UNPINNED for those three target functions: the reference holds no implementation, test or stored output of
-the diagonal Gaussian and the logistic regression, and its Stock-Watson density lives in a Stan model evaluated
+PARITY UNPINNED for those four target functions: the reference holds no implementation, test or stored output of
+the diagonal / dense-precision Gaussians and the logistic regression, and its Stock-Watson density lives in a Stan model evaluated
 through bridgestan (absent here: no stanc, no bridgestan; WALNUTSpy_examples/StockWatson/mainSW.py:15-26), so
 make_stock_watson() follows sw_innov.stan:2-52 line by line and is checked by finite differences only
 (tests/test_oracle_golden.py).  Everything else in oracle/ -- the transition kernels, the integrators, the adaptation,

@@ -93,40 +93,17 @@ static bool pick_plan_family(const wn_config& c, LaunchPlan& p) {
     case WN_TARGET_DIAG_GAUSS: {
       if constexpr (FAM == FAM_WPY || FAM == FAM_NUTS) {
         if (c.d > 512 && c.d <= 1024) {
-          // BASELINE config 2 (d = 1000): 128 threads x 8 coordinates, 4 blocks / SM (128 registers);
-          // WN_VARIANT selects the alternatives measured in DESIGN.md section 6 (tuning only)
+          // BASELINE config 2 (d = 1000); WN_VARIANT selects alternatives kept for comparison (measured in DESIGN.md
+          // section 6; tuning only)
           const char* v = getenv("WN_VARIANT");
           switch (v ? atoi(v) : 0) {
-            case 1: p = plan_plain<FAM, DiagT, 64, 8, 64, 1>(); return true;
-            case 2: p = plan_plain<FAM, DiagT, 128, 4, 128, 3>(); return true;
-            case 3: p = plan_plain<FAM, DiagT, 256, 2, 256, 2>(); return true;    // 8 warps per chain, 16 warps / SM
-            case 4: p = plan_plain<FAM, DiagT, 256, 2, 256, 4>(); return true;    // ... 32 warps / SM (64 registers)
-            case 5: p = plan_plain<FAM, DiagT, 64, 8, 64, 6>(); return true;      // 2 warps per chain, 12 warps / SM
-            case 6: p = plan_plain<FAM, DiagT, 128, 4, 128, 4>(); return true;
-            case 7: p = plan_plain<FAM, DiagT, 128, 4, 128, 5>(); return true;    // 5 blocks / SM (96 registers)
-            case 8: case 9: case 10:
-              // plain NUTS with ONE warp per chain (32 coordinates per lane, inverse variances in shared memory, gradient
-              // recomputed): no replicated scalar work, no block barriers
-              if constexpr (FAM == FAM_NUTS) {
-                const int var = atoi(v);
-                if (var == 8) p = plan_plain<FAM, DiagSmT, 32, 16, 64, 3, false, 2>();   // 6 chains / SM, two levels in smem
-                else if (var == 9) p = plan_plain<FAM, DiagSmT, 32, 16, 64, 4>();
-                else p = plan_plain<FAM, DiagSmT, 32, 16, 128, 2>();
-                return true;
-              }
-              break;
-            case 11: case 12:
-              if constexpr (FAM == FAM_NUTS) {
-                if (atoi(v) == 11) p = plan_plain<FAM, DiagT, 128, 4, 128, 3, false, 2>();
-                else p = plan_plain<FAM, DiagT, 128, 4, 128, 3, false, 3>();
-                return true;
-              }
-              break;
+            case 1: p = plan_plain<FAM, DiagT, 64, 8, 64, 1>(); return true;      // 2 warps per chain
+            case 2: p = plan_plain<FAM, DiagT, 128, 4, 128, 3>(); return true;    // 4 warps per chain, 3 blocks / SM
             default:
-              // D / R2P: 128 threads x 8 coordinates, 4 blocks / SM at 124 registers.  Plain NUTS (level loop): ONE
+              // D / R2P: 128 threads x 8 coordinates, 4 blocks / SM at 126 registers.  Plain NUTS (level loop): ONE
               // warp per chain, 32 coordinates per lane, inverse variances in shared memory, gradient recomputed
-              // (DiagSmT) -- no replicated scalar work, no block barrier per leaf pair: 4.05e8 grad evals/s against
-              // 3.5e8 for 4 warps per chain at 168 registers (WN_VARIANT=2 / 11 / 12) and 1.68e8 for the flat loop
+              // (DiagSmT) -- no replicated scalar work, no block barrier per leaf pair: 4.8e8 grad evals/s against
+              // 3.5e8 for 4 warps per chain (WN_VARIANT=2) and 1.68e8 for the flat loop of round 1
               if constexpr (FAM == FAM_NUTS) p = plan_plain<FAM, DiagSmT, 32, 16, 64, 4>();
               else p = plan_plain<FAM, DiagT, 128, 4, 128, 4>();
               return true;
@@ -177,11 +154,12 @@ static bool pick_plan_family(const wn_config& c, LaunchPlan& p) {
       const int T = c.d / 3;
       if (T <= 64 * 4) {
         // 6 blocks / SM (168 registers, 12 warps) measured 9 % faster than 4 blocks at 255 registers
-        // (8 blocks / SM at 128 registers: spills, same throughput)
+        // (8 blocks / SM at 128 registers: spills, same throughput); round 2: see below
         if constexpr (FAM == FAM_WPY || FAM == FAM_NUTS) {
           const char* v = getenv("WN_VARIANT");
-          if (v && atoi(v) == 1) p = plan_plain<FAM, StockWatsonT, 64, 7, 64, 5>();     // 5 blocks / SM, 200 registers
-          else p = plan_plain<FAM, StockWatsonT, 64, 7, 64, 6>();
+          // measured (C5 shape, R2P): launch bounds for 5 blocks / SM 2.65e8, for 6 blocks / SM 2.53e8 grad evals/s
+          if (v && atoi(v) == 1) p = plan_plain<FAM, StockWatsonT, 64, 7, 64, 6>();
+          else p = plan_plain<FAM, StockWatsonT, 64, 7, 64, 5>();
         }
         else p = plan_for<FAM, StockWatsonT, 64, 7, 64>();
         return true;

@@ -483,7 +483,7 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
   auto nuts_level = [&]() {
     if constexpr (NUTS_FAST) {
       const int level = C.level, side = C.side;
-      const double xi = C.xi, H0 = C.H0;
+      const double H0 = C.H0;
       const uint32_t n_new = C.n_new;
       const double jlo = C.jlo, jhi = C.jhi;
       auto jitl = [&](double u) -> double { return __dadd_rn(jlo, __dmul_rn(__dadd_rn(jhi, -jlo), u)); };
@@ -502,55 +502,78 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
       uint32_t nleaf = 0;
       unsigned long long nF = 0;
       int out = 0;   // 0: level complete, 1: forced reject, 2: sub-U-turn
-      // left-end slot `lvl` (>= 1): (q, xi v) in forward-time convention, as the L2 stack of the flat loop
+      // scratch vectors of this chain: pair e2 of vector vi at scv(vi)[e2 * sstride] (one 64-bit address computation
+      // per vector instead of one per pair)
+      const size_t sstride = (size_t)P.nslot * G;
+      auto scv = [&](int vi) -> double2* { return sc(vi, 0); };
+      // left-end slot `lvl` (>= 1): (q, v) with v in the INTEGRATION convention of the level (forward-time velocity
+      // = xi v).  With tmp = qp - qm = xi (q - ql) both products of the U-turn criterion lose their signs:
+      // v_cur(fwd).tmp = (xi v).(xi (q - ql)) = v.(q - ql) and v_left(fwd).tmp = (xi vl).(xi (q - ql)) = vl.(q - ql),
+      // exactly (multiplications by +-1 are exact), so neither the stores nor the checks multiply by xi.
       auto put_left = [&](int lvl) {
         if (lvl <= NSM) {
           double* b = ck + (size_t)(lvl - 1) * 2 * E * NT + tid;
 #pragma unroll
-          for (int e = 0; e < E; ++e) { b[e * NT] = q[e]; b[(E + e) * NT] = xi * v[e]; }
+          for (int e = 0; e < E; ++e) { b[e * NT] = q[e]; b[(E + e) * NT] = v[e]; }
         } else {
+          double2* pq = scv(V_STACK + 2 * lvl);
+          double2* pv = pq + E2 * sstride;
 #pragma unroll
           for (int e2 = 0; e2 < E2; ++e2) {
-            *sc(V_STACK + 2 * lvl, e2) = make_double2(q[2 * e2], q[2 * e2 + 1]);
-            *sc(V_STACK + 2 * lvl + 1, e2) = make_double2(xi * v[2 * e2], xi * v[2 * e2 + 1]);
+            pq[e2 * sstride] = make_double2(q[2 * e2], q[2 * e2 + 1]);
+            pv[e2 * sstride] = make_double2(v[2 * e2], v[2 * e2 + 1]);
           }
         }
       };
       // partial sums of the U-turn criterion (WALNUTS.py:95-97) between the registers and left-end slot `lvl`:
-      // a = v . (q - ql), b = vl . (q - ql)   (signs factored out, see uturn_vs)
+      // a = v . (q - ql), b = vl . (q - ql); U-turn iff a < 0 or b < 0
       auto dots_left = [&](int lvl, double& a, double& b) {
-        double a0 = 0.0, b0 = 0.0;
+        // (four interleaved partial sums per dot product when a lane holds many coordinates: a single accumulator would
+        //  be one dependent FMA chain of length E)
+        constexpr int NA = (E >= 16) ? 4 : 1;
+        double a0[NA], b0[NA];
+#pragma unroll
+        for (int k = 0; k < NA; ++k) { a0[k] = 0.0; b0[k] = 0.0; }
         if (lvl <= NSM) {
           const double* p = ck + (size_t)(lvl - 1) * 2 * E * NT + tid;
 #pragma unroll
           for (int e = 0; e < E; ++e) {
             const double tt = q[e] - p[e * NT];
-            a0 = fma(v[e], tt, a0);
-            b0 = fma(p[(E + e) * NT], tt, b0);
+            a0[e % NA] = fma(v[e], tt, a0[e % NA]);
+            b0[e % NA] = fma(p[(E + e) * NT], tt, b0[e % NA]);
           }
         } else {
+          const double2* pq = scv(V_STACK + 2 * lvl);
+          const double2* pv = pq + E2 * sstride;
 #pragma unroll
           for (int e2 = 0; e2 < E2; ++e2) {
-            const double2 ql = *sc(V_STACK + 2 * lvl, e2), vl = *sc(V_STACK + 2 * lvl + 1, e2);
+            const double2 ql = pq[e2 * sstride], vl = pv[e2 * sstride];
             const double t0 = q[2 * e2] - ql.x, t1 = q[2 * e2 + 1] - ql.y;
-            a0 = fma(v[2 * e2], t0, a0);
-            a0 = fma(v[2 * e2 + 1], t1, a0);
-            b0 = fma(vl.x, t0, b0);
-            b0 = fma(vl.y, t1, b0);
+            a0[(2 * e2) % NA] = fma(v[2 * e2], t0, a0[(2 * e2) % NA]);
+            a0[(2 * e2 + 1) % NA] = fma(v[2 * e2 + 1], t1, a0[(2 * e2 + 1) % NA]);
+            b0[(2 * e2) % NA] = fma(vl.x, t0, b0[(2 * e2) % NA]);
+            b0[(2 * e2 + 1) % NA] = fma(vl.y, t1, b0[(2 * e2 + 1) % NA]);
           }
         }
-        a = a0;
-        b = b0;
+        if constexpr (NA == 4) {
+          a = (a0[0] + a0[1]) + (a0[2] + a0[3]);
+          b = (b0[0] + b0[1]) + (b0[2] + b0[3]);
+        } else {
+          a = a0[0];
+          b = b0[0];
+        }
       };
       // proposal slot <- left-end slot `lvl` (the picked state is the first leaf of the pair)
       auto prop_from_left = [&](int lvl) {
+        double2* dst = scv(pvec);
         if (lvl <= NSM) {
           const double* p = ck + (size_t)(lvl - 1) * 2 * E * NT + tid;
 #pragma unroll
-          for (int e2 = 0; e2 < E2; ++e2) *sc(pvec, e2) = make_double2(p[(2 * e2) * NT], p[(2 * e2 + 1) * NT]);
+          for (int e2 = 0; e2 < E2; ++e2) dst[e2 * sstride] = make_double2(p[(2 * e2) * NT], p[(2 * e2 + 1) * NT]);
         } else {
+          const double2* src = scv(V_STACK + 2 * lvl);
 #pragma unroll
-          for (int e2 = 0; e2 < E2; ++e2) *sc(pvec, e2) = *sc(V_STACK + 2 * lvl, e2);
+          for (int e2 = 0; e2 < E2; ++e2) dst[e2 * sstride] = src[e2 * sstride];
         }
       };
       // bookkeeping of one leaf with energy Hl, step h and weight Wnew = exp(-Hl + H0) (lwtSum = 0 for fixedLeapFrog,
@@ -628,8 +651,9 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
             if (!leaf_book(x[0], hA, WA, rA, pick)) { out = 1; break; }
             if (pick) {
               if (level == 0) {
+                double2* dst = scv(pvec);
 #pragma unroll
-                for (int e2 = 0; e2 < E2; ++e2) *sc(pvec, e2) = make_double2(q[2 * e2], q[2 * e2 + 1]);
+                for (int e2 = 0; e2 < E2; ++e2) dst[e2 * sstride] = make_double2(q[2 * e2], q[2 * e2 + 1]);
               } else {
                 prop_from_left(lvlA);
               }
@@ -637,11 +661,12 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
             if (level == 0) break;
             if (!leaf_book(x[1], hB, WB, rB, pick)) { out = 1; break; }
             if (pick) {
+              double2* dst = scv(pvec);
 #pragma unroll
-              for (int e2 = 0; e2 < E2; ++e2) *sc(pvec, e2) = make_double2(q[2 * e2], q[2 * e2 + 1]);
+              for (int e2 = 0; e2 < E2; ++e2) dst[e2 * sstride] = make_double2(q[2 * e2], q[2 * e2 + 1]);
             }
           }
-          sub = (x[2] < 0.0) || (xi * x[3] < 0.0);
+          sub = (x[2] < 0.0) || (x[3] < 0.0);
           if (sub || sp + 1 > level || (nleaf & ((1u << (sp + 1)) - 1u)) != 0u) break;
           const uint32_t m = nleaf - (1u << (sp + 1)) + 1u;      // left end of the next larger span ending here
           lvl = (m == 1u) ? level : (__ffs(m - 1u) - 1);
