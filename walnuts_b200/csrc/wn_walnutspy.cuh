@@ -52,6 +52,8 @@ struct RunParams {
   // integratorAuxPar fields of the extended integrators (adaptiveIntegrators.py:36-44); EXT kernels only
   int maxFPiter;
   double FPtol, gradThresh;
+  int tune;              // tuning switches (environment WN_TUNE, read at launch; none in use: an L1 prefetch of the
+                         // deeper left ends under the leapfrog steps measured 3 % slower)
 };
 #define WN_ADAPT_STRIDE 16
 
@@ -528,9 +530,7 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
       // partial sums of the U-turn criterion (WALNUTS.py:95-97) between the registers and left-end slot `lvl`:
       // a = v . (q - ql), b = vl . (q - ql); U-turn iff a < 0 or b < 0
       auto dots_left = [&](int lvl, double& a, double& b) {
-        // (four interleaved partial sums per dot product when a lane holds many coordinates: a single accumulator would
-        //  be one dependent FMA chain of length E)
-        constexpr int NA = (E >= 16) ? 4 : 1;
+        constexpr int NA = 1;   // (four interleaved sums measured slower at 254 registers: 4.48e8 against 4.80e8)
         double a0[NA], b0[NA];
 #pragma unroll
         for (int k = 0; k < NA; ++k) { a0[k] = 0.0; b0[k] = 0.0; }
