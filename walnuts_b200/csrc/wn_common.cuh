@@ -85,7 +85,10 @@ struct Group {
     else return ((1u << G) - 1u) << ((threadIdx.x & 31u) & ~(unsigned)(G - 1));
   }
 
-  // red: shared scratch of 2*WARPS*NV doubles (G > 32 only: one chain per block)
+  // red: shared scratch of 2 * WARPS * 8 doubles (G > 32 only: one chain per block), two halves used alternately
+  // (`parity`).  EVERY reduction, whatever its number of values, takes the half at red + parity * WARPS * 8: with a
+  // value-count-dependent offset the half of one reduction overlapped the other half of the previous one, and a warp
+  // that had passed the barrier could overwrite partial sums a slower warp was still reading (racecheck, round 2).
   template <int NV>
   __device__ __forceinline__ static void sum(double (&x)[NV], double* red, int& parity) {
     if constexpr (G == 1) {
@@ -99,7 +102,7 @@ struct Group {
       }
       if constexpr (G > 32) {
         const int w = threadIdx.x >> 5;
-        double* buf = red + parity * (WARPS * NV);
+        double* buf = red + parity * (WARPS * 8);
         if ((threadIdx.x & 31) == 0) {
 #pragma unroll
           for (int k = 0; k < NV; ++k) buf[w * NV + k] = x[k];
@@ -135,7 +138,7 @@ struct Group {
     // lane l < 4 holds value 2 (l & 1) + (l >> 1)
     if constexpr (G > 32) {
       const int w = threadIdx.x >> 5;
-      double* buf = red + parity * (WARPS * 4);
+      double* buf = red + parity * (WARPS * 8);
       if (lane < 4u) buf[w * 4 + 2 * (lane & 1u) + (lane >> 1)] = k;
       __syncthreads();
 #pragma unroll
@@ -166,7 +169,7 @@ struct Group {
       flags = __reduce_or_sync(m, flags);
       if constexpr (G > 32) {
         const int w = threadIdx.x >> 5;
-        double* buf = red + parity * (WARPS * 2);
+        double* buf = red + parity * (WARPS * 8);
         if ((threadIdx.x & 31) == 0) {
           buf[w * 2] = x;
           buf[w * 2 + 1] = __hiloint2double(0, (int)flags);
@@ -201,7 +204,7 @@ struct Group {
       }
       if constexpr (G > 32) {
         const int w = threadIdx.x >> 5;
-        double* buf = red + parity * (WARPS * NV);
+        double* buf = red + parity * (WARPS * 8);
         if ((threadIdx.x & 31) == 0) {
 #pragma unroll
           for (int k = 0; k < NV; ++k) buf[w * NV + k] = x[k];

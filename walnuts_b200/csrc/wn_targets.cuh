@@ -648,7 +648,12 @@ struct LogRegCoopT {
     bool nl[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) { any = any || (act[c] != 0.0); nl[c] = need[c] != 0.0; }
-    if (!any) return;
+    if (!any) {
+      // no chain of the CTA is in a pass: leave through a barrier, so that no warp can publish the NEXT trip's flags
+      // while another one is still reading this trip's
+      __syncthreads();
+      return;
+    }
     double acc[4][C];
 #pragma unroll
     for (int j = 0; j < 4; ++j)
@@ -975,7 +980,12 @@ struct LogRegMmaTP {
     bool any = false, anyneed = false;
 #pragma unroll
     for (int c = 0; c < C; ++c) { any = any || (act[c] != 0.0); anyneed = anyneed || (need[c] != 0.0); }
-    if (!any) return;
+    if (!any) {
+      // no chain of the CTA is in a pass: leave through a barrier, so that no warp can publish the NEXT trip's flags
+      // while another one is still reading this trip's
+      __syncthreads();
+      return;
+    }
     const bool nl0 = need[2 * lc] != 0.0, nl1 = need[2 * lc + 1] != 0.0;
     // beta as B fragments: B[k = 4 kk + lc][n = chain lr]
     double bf[KS];
@@ -1254,7 +1264,12 @@ struct DenseGaussMmaTP {
     bool any = false;
 #pragma unroll
     for (int c = 0; c < C; ++c) any = any || (act[c] != 0.0);
-    if (!any) return;
+    if (!any) {
+      // no chain of the CTA is in a pass: leave through a barrier, so that no warp can publish the NEXT trip's flags
+      // while another one is still reading this trip's
+      __syncthreads();
+      return;
+    }
     double bf[KS];                                   // Q as B fragments: B[k = 4 kk + lc][n = chain lr]
 #pragma unroll
     for (int kk = 0; kk < KS; ++kk) bf[kk] = bs[(4 * kk + lc) * C + lr];
