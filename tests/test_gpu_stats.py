@@ -187,3 +187,40 @@ def test_multi_gpu_multi_process_comm(cuda_lib):
         for j in range(3):
             e, r = diagnostics.ess_bulk(x[:, :, j].T)
             assert abs(ess[j] - e) <= 1e-8 * e and abs(rhat[j] - r) <= 1e-10
+
+
+def test_devices_argument_single_gpu(cuda_lib):
+    """`devices=[0]` is the plain call; the sharding helper splits chains contiguously with global chain ids."""
+    import walnuts_b200 as wb
+    from walnuts_b200.api import _over_devices
+    q0 = np.random.default_rng(5).standard_normal((9, 5))
+    kw = dict(integrator=wb.adaptLeapFrogD, H0=0.6, delta0=0.3, numIter=10, warmupIter=0, M=5, adaptH=False,
+              adaptDelta=False, seed=4)
+    s1, d1 = wb.WALNUTS(wb.targets.stdGauss, q0, **kw)
+    s2, d2 = wb.WALNUTS(wb.targets.stdGauss, q0, devices=[0], **kw)
+    assert np.array_equal(s1, s2) and np.array_equal(d1, d2)
+    # the same GPU used as two "devices": shards of 5 + 4 chains with chain offsets 0 and 5 reproduce the single call
+    parts = _over_devices(lambda xs, dev, off: wb.WALNUTS(wb.targets.stdGauss, xs, device=0, chain_offset=off, **kw),
+                          q0, [0, 0], 0)
+    assert np.array_equal(np.concatenate([p[0] for p in parts]), s1)
+
+
+def test_d4096_single_cta_chain(cuda_lib):
+    """d = 4096 (one 16-warp CTA per chain): free-running parity with the C oracle for the three integrators."""
+    from oracle import c_oracle
+    from tests.helpers import close
+    from walnuts_b200 import ChainBatch
+    d = 4096
+    rng = np.random.default_rng(8)
+    sigma = np.exp(rng.uniform(-1.0, 1.0, d))
+    q0 = rng.standard_normal((3, d)) * sigma
+    iv = 1.0 / sigma ** 2
+    for integ, H0 in (("fixed", 0.05), ("D", 0.25), ("R2P", 0.25)):
+        with ChainBatch("diag_gauss", d, 3, integrator=integ, H0=H0, delta=0.3, M=6, seed=11, data={"inv_var": iv}) as cb:
+            cb.set_state(q0)
+            out = cb.run(8, draws=True, diag=True)
+        for c in (0, 2):
+            dr, dg, ne = c_oracle.run_chain("diag_gauss", integ, q0[c], H0, 0.3, 6, 8, 11, c, inv_var=iv)
+            ok, err = close(out["draws"][:, c], dr, scale=sigma)
+            assert ok, (integ, err)
+            assert np.array_equal(out["diag"][:, c][:, [0, 1, 6, 7, 19]], dg[:, [0, 1, 6, 7, 19]])

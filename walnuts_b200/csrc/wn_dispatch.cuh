@@ -74,6 +74,7 @@ static bool pick_generic(int d, LaunchPlan& p) {
   WN_PICK(32, 8, 128)
   WN_PICK(64, 8, 64)
   WN_PICK(256, 4, 256)
+  WN_PICK(512, 4, 512)     // d <= 4096: one 16-warp CTA per chain, one CTA per SM
   return false;
 }
 template <int FAM, template <int, int> class T>
