@@ -19,7 +19,7 @@ Restates reference walnuts/walnuts.py:16-33 (uturn), :62-70 (sub_uturn), :74-95 
 stores forward-time momenta and draws ell from {max(1, ell_s//2), ell_s, 2 ell_s}.
 
 The rng shim `KeyedPackageRNG` feeds the REAL walnuts.py the same keyed Philox draws; it is
-what tests/golden/make_golden.py and tests/test_oracle_vs_reference.py use.
+what tests/golden/make_golden.py and tests/test_oracle_golden.py use.
 """
 import math
 

@@ -142,3 +142,28 @@ def test_user_target_package_mode(cuda_lib, name):
             k += 1
         # the Gaussian agrees over the whole run; the quartic density until its dynamics amplify rounding
         assert k == n_iter if name == "correlated_normal" else k >= 4, (k, draws[:k + 1], ref[:k + 1])
+
+
+def test_user_target_d200_warp_per_chain(cuda_lib):
+    """64 < d <= 512: one warp per chain (the user's sequential function evaluated by every lane on the whole vector in
+    shared memory); same draws as the built-in diagonal Gaussian, WALNUTSpy and package semantics."""
+    import walnuts_b200 as wb
+    d = 200
+    sigma = np.logspace(-1, 1, d)
+    src = """
+    WN_TARGET_LP_GRAD(q, g, data, n_data) {
+      double lp = 0.0;
+      for (int i = 0; i < WN_D; ++i) { g[i] = -q[i] * data[i]; lp += q[i] * g[i]; }
+      return 0.5 * lp;
+    }"""
+    tg = wb.targets.cuda_target(src, d, data=1.0 / sigma ** 2, name="my_diag200")
+    q0 = np.random.default_rng(2).standard_normal((9, d)) * sigma
+    for ig, H0 in ((wb.adaptLeapFrogR2P, 0.2), (wb.fixedLeapFrog, 0.05), (wb.adaptYoshidaD, 0.3)):
+        kw = dict(integrator=ig, H0=H0, delta0=0.3, numIter=10, warmupIter=0, M=6, adaptH=False, adaptDelta=False, seed=12)
+        s1, d1 = wb.WALNUTS(tg, q0, **kw)
+        s2, d2 = wb.WALNUTS(wb.targets.diag_gauss(sigma), q0, **kw)
+        ok, err = close(s1, s2, axis=-2)
+        assert ok, (ig, err)
+        assert np.array_equal(d1[..., EXACT], d2[..., EXACT]), ig
+    with pytest.raises(ValueError):
+        wb.targets.cuda_target(src, 513)

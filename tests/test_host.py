@@ -131,3 +131,49 @@ def test_bench_reference_arm_contract():
     assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] == line["value"] and "sample" in cb
     assert line["e2e"] == {"value": line["value"], "unit": "grad_evals/s", "h2d_bytes_per_step": 0,
                            "d2h_bytes_per_step": 0}
+
+
+def test_index_generator_detection():
+    """recordOrbitStats + generated: only coordinate selections are accepted (api._index_generator); pure host logic."""
+    from walnuts_b200.api import _index_generator
+    assert list(_index_generator(lambda q: np.array([q[0], q[1]]), 11)) == [0, 1]       # mainFunnel.py:19-20
+    assert list(_index_generator(lambda q: q[[3, 0, 3]], 5)) == [3, 0, 3]
+    assert list(_index_generator(lambda q: q, 4)) == [0, 1, 2, 3]
+    assert _index_generator(lambda q: 2.0 * q, 4) is None
+    assert _index_generator(lambda q: np.array([q[0] + q[1]]), 4) is None
+    assert _index_generator(lambda q: np.array([np.exp(q[0])]), 4) is None
+    assert _index_generator(lambda q: 1 / 0, 4) is None
+
+
+def test_device_sharding_is_contiguous_with_global_chain_ids():
+    """WALNUTS(..., devices=[...]): contiguous blocks of chains, chain_offset = first global chain id of the block."""
+    from walnuts_b200.api import _over_devices
+    x = np.arange(10 * 3, dtype=np.float64).reshape(10, 3)
+    seen = _over_devices(lambda xs, dev, off: (dev, off, xs.copy()), x, [0, 1, 2], 100)
+    assert [s[0] for s in seen] == [0, 1, 2]
+    assert [s[1] for s in seen] == [100, 103, 106]
+    assert np.array_equal(np.concatenate([s[2] for s in seen]), x)
+    # fewer chains than devices: one chain per device, the rest unused
+    seen = _over_devices(lambda xs, dev, off: (dev, off, xs.shape[0]), x[:2], [0, 1, 2, 3], 0)
+    assert seen == [(0, 0, 1), (1, 1, 1)]
+
+
+def test_bench_workloads_are_the_baseline_configs():
+    """bench.py's workload table: shapes of BASELINE.json's five configs (host logic only)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    W = bench.WORKLOADS
+    assert (W["c2"]["d"], W["c2"]["chains"], W["c2"]["integrator"]) == (1000, 65536, "R2P")
+    assert (W["c1"]["d"], W["c1"]["mode"], W["c1"]["H0"], W["c1"]["M"], W["c1"]["delta"]) == (100, "package", 2.0, 10, 0.1)
+    assert (W["c3"]["d"], W["c3"]["chains"], W["c3"]["M"]) == (11, 262144, 12)
+    assert (W["c4"]["d"], W["c4"]["chains"]) == (100, 16384)
+    assert (W["c5"]["d"], W["c5"]["chains"] * 8, W["c5"]["M"], W["c5"]["minC"]) == (756, 1048576, 14, 3)
+    assert W["c2_1m"]["chains"] == 1048576
+    for name in ("c1", "c3", "c5"):
+        q0, data = bench.make_inputs(W[name], 7, 0)
+        assert q0.shape == (7, W[name]["d"]) and np.isfinite(q0).all()
+    s = bench.sigma_vec()
+    assert s.shape == (1000,) and np.isclose(s.min(), 1e-2) and np.isclose(s.max(), 1e2)
+    assert np.isclose(s[0], 1e-2) and np.isclose(s[bench.MONITOR - 1], 1e2)      # monitored coordinates span the range

@@ -159,6 +159,7 @@ static bool pick_plan_family(const wn_config& c, LaunchPlan& p) {
         if constexpr (FAM == FAM_WPY || FAM == FAM_NUTS) {
           const char* v = getenv("WN_VARIANT");
           // measured (C5 shape, R2P): launch bounds for 5 blocks / SM 2.65e8, for 6 blocks / SM 2.53e8 grad evals/s
+          // (4 warps per chain with 2 time steps per thread, 128 / 96 registers: the same 2.63e8)
           if (v && atoi(v) == 1) p = plan_plain<FAM, StockWatsonT, 64, 7, 64, 6>();
           else p = plan_plain<FAM, StockWatsonT, 64, 7, 64, 5>();
         }

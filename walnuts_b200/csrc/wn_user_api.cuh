@@ -8,7 +8,8 @@
 //     }
 //
 // which walnuts_b200.targets.cuda_target() compiles with nvcc for sm_100a into a plug-in library next to the
-// sampler kernels (one thread per chain; WN_D <= 64).  This header is included BEFORE the user's source.
+// sampler kernels (WN_D <= 64: one thread per chain; 64 < WN_D <= 512: one warp per chain, the function is then called by
+// every lane with q and g in shared memory).  This header is included BEFORE the user's source.
 #pragma once
 #include <cmath>
 #include <cstdint>

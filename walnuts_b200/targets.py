@@ -88,13 +88,14 @@ def cuda_target(source, d, data=None, name="user", verbose=False):
         }
 
     It is compiled once with nvcc for sm_100a into walnuts_b200/_lib/user/<hash>.so (cached by content), linked
-    against the same persistent kernels as the built-in targets (one thread per chain, d <= 64), and serves
+    against the same persistent kernels as the built-in targets (d <= 64: one thread per chain; 64 < d <= 512: one warp
+    per chain -- leapfrog and tree logic parallel over the lanes, the user's function evaluated on the whole vector), and serves
     WALNUTS(...) with every integrator and the warm-up adaptation as well as walnuts(...) / walnuts_step(...)."""
     from . import build as _build
     d = int(d)
-    if not 1 <= d <= 64:
-        raise ValueError("cuda_target: 1 <= d <= 64 (one thread per chain holds the whole vector; beyond d ~ 24 "
-                         "the state spills from registers to thread-local memory)")
+    if not 1 <= d <= 512:
+        raise ValueError("cuda_target: 1 <= d <= 512 (d <= 64: one thread per chain holds the whole vector; "
+                         "64 < d <= 512: one warp per chain, the density evaluated by every lane on the whole vector)")
     csrc = os.path.join(_build.HERE, "csrc")
     tu = (f"#define WN_USER_D {d}\n#include \"wn_user_api.cuh\"\n#line 1 \"{name}\"\n{source}\n"
           "#include \"wn_user_plugin.cuh\"\n")
