@@ -224,3 +224,33 @@ def test_d4096_single_cta_chain(cuda_lib):
             ok, err = close(out["draws"][:, c], dr, scale=sigma)
             assert ok, (integ, err)
             assert np.array_equal(out["diag"][:, c][:, [0, 1, 6, 7, 19]], dg[:, [0, 1, 6, 7, 19]])
+
+
+@pytest.mark.parametrize("mode", ["walnutspy", "package"])
+def test_longest_first_queue_order_is_a_hint_only(cuda_lib, mode):
+    """wn_sched.cu: from the second call on a handle the chain queue is served in descending order of the previous
+    call's evaluation counts.  More chains than resident slots, three calls of three transitions against ONE call of
+    nine (which has no history, hence the natural order): bit-identical draws, counters and final states."""
+    from walnuts_b200 import ChainBatch
+    n, d = 40000, 11
+    rng = np.random.default_rng(12)
+    q0 = rng.standard_normal((n, d))
+    q0[:, 0] *= 3.0
+    q0[:, 1:] *= np.exp(0.5 * q0[:, :1])
+    if mode == "walnutspy":
+        kw = dict(integrator="R2P", H0=0.3, delta=0.3, M=8, seed=5)
+    else:
+        kw = dict(mode="package", H0=0.5, delta=0.3, M=6, seed=5, data={"inv_mass": np.ones(d)})
+    target = "funnel" if mode == "walnutspy" else "funnel_pkg"
+    with ChainBatch(target, d, n, **kw) as cb:
+        cb.set_state(q0)
+        whole = cb.run(9, draws=True)
+        q_whole = cb.get_state()
+    with ChainBatch(target, d, n, **kw) as cb:
+        cb.set_state(q0)
+        parts = [cb.run(3, draws=True) for _ in range(3)]
+        q_parts = cb.get_state()
+    assert np.array_equal(np.concatenate([p["draws"] for p in parts]), whole["draws"])
+    assert np.array_equal(sum(p["nevalF"] for p in parts), whole["nevalF"])
+    assert np.array_equal(q_parts, q_whole)
+    assert len(np.unique(parts[0]["nevalF"])) > 10          # the costs do differ between chains: the order is not trivial

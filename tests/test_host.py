@@ -64,7 +64,7 @@ def test_user_target_plugin_builds_and_registers(cuda_lib):
     with pytest.raises(ValueError):
         wb.targets.resolve(tg, 3)
     with pytest.raises(ValueError):
-        wb.targets.cuda_target("", 65)
+        wb.targets.cuda_target("", 513)
     with pytest.raises(RuntimeError, match="nvcc failed"):
         wb.targets.cuda_target("WN_TARGET_LP_GRAD(q, g, data, n_data) { return undefined_symbol; }", 2, name="broken")
     assert cuda_lib.wn_register_user_target(b"/nonexistent.so") < 0

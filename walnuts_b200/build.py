@@ -13,7 +13,7 @@ LIB_DIR = os.path.join(HERE, "_lib")
 OBJ_DIR = os.path.join(LIB_DIR, "obj")
 LIB_PATH = os.path.join(LIB_DIR, "libwalnuts_b200.so")
 SOURCES = [os.path.join(HERE, "csrc", f) for f in
-           ("capi.cu", "wn_stats.cu", "plans_wpy.cu", "plans_nuts.cu", "plans_pkg.cu", "plans_adapt.cu", "plans_ext.cu")]
+           ("capi.cu", "wn_stats.cu", "wn_sched.cu", "plans_wpy.cu", "plans_nuts.cu", "plans_pkg.cu", "plans_adapt.cu", "plans_ext.cu")]
 HEADERS = [os.path.join(HERE, "csrc", f) for f in
            ("wn_common.cuh", "wn_targets.cuh", "wn_walnutspy.cuh", "wn_package.cuh", "wn_dispatch.cuh", "wn_handle.hpp")] + \
           [os.path.join(ROOT, "include", "walnuts_cuda.h")]

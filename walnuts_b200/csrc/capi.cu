@@ -193,6 +193,7 @@ void wn_destroy(wn_handle* h) {
     cudaStreamSynchronize(h->stream);
   }
   cudaFree(h->d_state); cudaFree(h->d_scratch); cudaFree(h->d_queue); cudaFree(h->d_totals);
+  wn_sched_free(h);
   cudaFree(h->o_draws); cudaFree(h->o_diag); cudaFree(h->o_lo); cudaFree(h->o_hi); cudaFree(h->o_f); cudaFree(h->o_b);
   cudaFree(h->d_p0); cudaFree(h->d_p1); cudaFree(h->d_p2); cudaFree(h->d_inv_mass); cudaFree(h->d_H); cudaFree(h->d_delta); cudaFree(h->d_adapt_state); cudaFree(h->d_adapt_hist);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -421,6 +422,13 @@ static int run_async_impl(wn_handle* h, int64_t n_iter, double* d_draws, double*
     h->adapt_exported = true;
   }
   CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
+  // queue order of this call: the chains that were longest in the previous call first (wn_sched.cu)
+  // -- for kernels whose chains share a warp (small d): there the per-chain cost is heavy-tailed and the gain measured
+  // (+3-4 % at config 3); with whole warps per chain it measured neutral (C2) to slightly negative (C4), so those keep
+  // the natural order
+  const unsigned int* order = nullptr;
+  if (p.G < 32)
+    if (const int src = wn_sched_prepare(h, nslot, 32 / p.G, &order)) return src;
   if (!p.package) {
     RunParams P;
     memset(&P, 0, sizeof(P));
@@ -440,7 +448,7 @@ static int run_async_impl(wn_handle* h, int64_t n_iter, double* d_draws, double*
     P.Hstep = h->d_H; P.delta = h->d_delta; P.state = h->d_state; P.draws = d_draws; P.diag = d_diag;
     P.orbit_min = d_omin; P.orbit_max = d_omax;
     P.nevalF = (unsigned long long*)d_nevalF; P.nevalB = (unsigned long long*)d_nevalB;
-    P.totals = h->d_totals; P.scratch = h->d_scratch; P.nslot = nslot; P.queue = h->d_queue; P.tp = tp;
+    P.totals = h->d_totals; P.scratch = h->d_scratch; P.nslot = nslot; P.queue = h->d_queue; P.order = order; P.cost = h->d_cost; P.tp = tp;
     void* args[] = {&P};
     if (ut) {
       const int rc = ut->launch(user_family(c), c.device, &P, (unsigned)blocks, h->stream);
@@ -458,7 +466,7 @@ static int run_async_impl(wn_handle* h, int64_t n_iter, double* d_draws, double*
     P.macro_step = c.H0; P.max_error = c.delta; P.inv_mass = h->d_inv_mass;
     P.state = h->d_state; P.draws = d_draws;
     P.neval = (unsigned long long*)d_nevalF; P.totals = h->d_totals;
-    P.scratch = h->d_scratch; P.nslot = nslot; P.queue = h->d_queue; P.tp = tp;
+    P.scratch = h->d_scratch; P.nslot = nslot; P.queue = h->d_queue; P.order = order; P.cost = h->d_cost; P.tp = tp;
     void* args[] = {&P};
     if (ut) {
       const int rc = ut->launch(user_family(c), c.device, &P, (unsigned)blocks, h->stream);
@@ -468,6 +476,7 @@ static int run_async_impl(wn_handle* h, int64_t n_iter, double* d_draws, double*
     }
   }
   CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
+  if (h->d_cost) h->have_cost = true;
   h->iter_done += (uint32_t)n_iter;
   h->last_launches = 1;
   return WN_OK;

@@ -42,6 +42,11 @@ struct wn_handle {
   double *o_draws = nullptr, *o_diag = nullptr, *o_lo = nullptr, *o_hi = nullptr;
   uint64_t *o_f = nullptr, *o_b = nullptr;
   size_t cap_draws = 0, cap_diag = 0, cap_lo = 0, cap_hi = 0;
+  // chain scheduling (wn_sched.cu): evaluations of every chain in the previous call -> launch order of the next one
+  unsigned int *d_cost = nullptr, *d_cost_sorted = nullptr, *d_iota = nullptr, *d_order = nullptr, *d_order_sorted = nullptr;
+  void* d_sort_tmp = nullptr;
+  size_t sort_tmp_bytes = 0;
+  bool have_cost = false;
   // cross-GPU statistics (wn_stats.cu): NCCL communicator of this handle's rank, or null
   void* comm = nullptr;
   int comm_rank = 0, comm_size = 1;
@@ -52,6 +57,10 @@ static inline int fail(wn_handle* h, int code, const std::string& msg) {
   if (h) h->err = msg;
   return code;
 }
+// wn_sched.cu: (re)builds h->d_order from h->d_cost on h->stream; *order = the queue order for this launch or null
+int wn_sched_prepare(wn_handle* h, int nslot, int chains_per_warp, const unsigned int** order);
+void wn_sched_free(wn_handle* h);
+
 #define CUDA_TRY(h, expr)                                                                \
   do {                                                                                   \
     cudaError_t _e = (expr);                                                             \

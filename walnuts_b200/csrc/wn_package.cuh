@@ -32,6 +32,8 @@ struct PkgParams {
   double2* scratch;
   int nslot;
   unsigned int* queue;
+  const unsigned int* order;    // see RunParams
+  unsigned int* cost;
   TargetParams tp;
 };
 
@@ -384,13 +386,17 @@ __global__ void __launch_bounds__(NT, MINB) package_kernel(const __grid_constant
         if (j < P.d) P.state[(size_t)cidx * P.d + j] = q[e];
       }
       if (t == 0 && P.neval) P.neval[cidx] = ce;
+      if (t == 0 && P.cost) P.cost[cidx] = (unsigned int)min(ce, 0xffffffffull);
       tot += ce;
       st = PS_CHAIN;
       break;
     } while (0);
     if (st == PS_CHAIN) do {
       uint32_t cidx = 0;
-      if (t == 0) cidx = atomicAdd(P.queue, 1u);
+      if (t == 0) {
+        cidx = atomicAdd(P.queue, 1u);
+        if (P.order && cidx < (uint32_t)P.n_chains) cidx = P.order[cidx];
+      }
       cidx = Grp::bcast0(cidx, &sh_bcast);
       if (cidx >= (uint32_t)P.n_chains) {
         st = PS_EXIT;

@@ -43,6 +43,8 @@ struct RunParams {
   double2* scratch;
   int nslot;
   unsigned int* queue;
+  const unsigned int* order;   // [n_chains] or null: the i-th chain taken from the queue (longest first, wn_sched.cu)
+  unsigned int* cost;          // [n_chains] or null: gradient evaluations of the chain in this call (next call's order)
   TargetParams tp;
   // warm-up adaptation (reference WALNUTS.py:136-147, 313, 701-712); ADAPT kernels only
   int warmup_iter, adaptH, adaptDelta;
@@ -1236,6 +1238,7 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
       if (t == 0) {
         if (P.nevalF) P.nevalF[cidx] = cf;
         if (P.nevalB) P.nevalB[cidx] = cbk;
+        if (P.cost) P.cost[cidx] = (unsigned int)min(cf + cbk, 0xffffffffull);
         if constexpr (ADAPT) if (P.adapt_state) {
           double* as = P.adapt_state + (size_t)cidx * WN_ADAPT_STRIDE;
           as[0] = C.Hbig; as[1] = C.delta; as[2] = (double)C.p2npush;
@@ -1251,7 +1254,10 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
     } while (0);
     if (st == ST_CHAIN) do {  // grab the next chain from the queue
       uint32_t cidx = 0;
-      if (t == 0) cidx = atomicAdd(P.queue, 1u);
+      if (t == 0) {
+        cidx = atomicAdd(P.queue, 1u);
+        if (P.order && cidx < (uint32_t)P.n_chains) cidx = P.order[cidx];
+      }
       cidx = Grp::bcast0(cidx, &sh_bcast);
       if (cidx >= (uint32_t)P.n_chains) {
         st = ST_EXIT;
