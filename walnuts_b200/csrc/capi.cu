@@ -448,7 +448,7 @@ static int run_async_impl(wn_handle* h, int64_t n_iter, double* d_draws, double*
     P.Hstep = h->d_H; P.delta = h->d_delta; P.state = h->d_state; P.draws = d_draws; P.diag = d_diag;
     P.orbit_min = d_omin; P.orbit_max = d_omax;
     P.nevalF = (unsigned long long*)d_nevalF; P.nevalB = (unsigned long long*)d_nevalB;
-    P.totals = h->d_totals; P.scratch = h->d_scratch; P.nslot = nslot; P.queue = h->d_queue; P.order = order; P.cost = h->d_cost; P.tp = tp;
+    P.totals = h->d_totals; P.scratch = h->d_scratch; P.nslot = nslot; P.queue = h->d_queue; P.order = order; P.order_len = order ? h->d_sched_meta + 1 : nullptr; P.cost = h->d_cost; P.tp = tp;
     void* args[] = {&P};
     if (ut) {
       const int rc = ut->launch(user_family(c), c.device, &P, (unsigned)blocks, h->stream);
@@ -466,7 +466,7 @@ static int run_async_impl(wn_handle* h, int64_t n_iter, double* d_draws, double*
     P.macro_step = c.H0; P.max_error = c.delta; P.inv_mass = h->d_inv_mass;
     P.state = h->d_state; P.draws = d_draws;
     P.neval = (unsigned long long*)d_nevalF; P.totals = h->d_totals;
-    P.scratch = h->d_scratch; P.nslot = nslot; P.queue = h->d_queue; P.order = order; P.cost = h->d_cost; P.tp = tp;
+    P.scratch = h->d_scratch; P.nslot = nslot; P.queue = h->d_queue; P.order = order; P.order_len = order ? h->d_sched_meta + 1 : nullptr; P.cost = h->d_cost; P.tp = tp;
     void* args[] = {&P};
     if (ut) {
       const int rc = ut->launch(user_family(c), c.device, &P, (unsigned)blocks, h->stream);

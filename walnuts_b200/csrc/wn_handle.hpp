@@ -44,6 +44,7 @@ struct wn_handle {
   size_t cap_draws = 0, cap_diag = 0, cap_lo = 0, cap_hi = 0;
   // chain scheduling (wn_sched.cu): evaluations of every chain in the previous call -> launch order of the next one
   unsigned int *d_cost = nullptr, *d_cost_sorted = nullptr, *d_iota = nullptr, *d_order = nullptr, *d_order_sorted = nullptr;
+  unsigned int* d_sched_meta = nullptr;   // [2]: exclusive warps K, queue length
   void* d_sort_tmp = nullptr;
   size_t sort_tmp_bytes = 0;
   bool have_cost = false;

@@ -33,6 +33,7 @@ struct PkgParams {
   int nslot;
   unsigned int* queue;
   const unsigned int* order;    // see RunParams
+  const unsigned int* order_len;
   unsigned int* cost;
   TargetParams tp;
 };
@@ -395,7 +396,7 @@ __global__ void __launch_bounds__(NT, MINB) package_kernel(const __grid_constant
       uint32_t cidx = 0;
       if (t == 0) {
         cidx = atomicAdd(P.queue, 1u);
-        if (P.order && cidx < (uint32_t)P.n_chains) cidx = P.order[cidx];
+        if (P.order) cidx = (cidx < *P.order_len) ? P.order[cidx] : 0xffffffffu;
       }
       cidx = Grp::bcast0(cidx, &sh_bcast);
       if (cidx >= (uint32_t)P.n_chains) {

@@ -43,7 +43,8 @@ struct RunParams {
   double2* scratch;
   int nslot;
   unsigned int* queue;
-  const unsigned int* order;   // [n_chains] or null: the i-th chain taken from the queue (longest first, wn_sched.cu)
+  const unsigned int* order;   // queue entries or null (wn_sched.cu): chain index, or 0xffffffff = this group retires
+  const unsigned int* order_len;   // device word: number of queue entries
   unsigned int* cost;          // [n_chains] or null: gradient evaluations of the chain in this call (next call's order)
   TargetParams tp;
   // warm-up adaptation (reference WALNUTS.py:136-147, 313, 701-712); ADAPT kernels only
@@ -1005,7 +1006,7 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
       const double tl = (level == 0) ? h : (side ? C.timeLen1 : C.timeLen0) + h;
       if (side) { C.maxInt1 = idx; C.timeLen1 = tl; C.endH1 = Hfwd; }
       else { C.maxInt0 = idx; C.timeLen0 = tl; C.endH0 = Hfwd; }
-      {  // running statistics over used steps
+      if (ADAPT || P.diag) {  // running statistics over used steps: diagnostics columns 8-11, 14, 16, 17, 21, 22; :704
         const int If = C.If, Ib = C.Ib;
         const int cs = is_fixed() ? 0 : C.cSim;
         if (C.sN == 0) {
@@ -1256,7 +1257,7 @@ __global__ void __launch_bounds__(NT, MINB) walnutspy_kernel(const __grid_consta
       uint32_t cidx = 0;
       if (t == 0) {
         cidx = atomicAdd(P.queue, 1u);
-        if (P.order && cidx < (uint32_t)P.n_chains) cidx = P.order[cidx];
+        if (P.order) cidx = (cidx < *P.order_len) ? P.order[cidx] : 0xffffffffu;
       }
       cidx = Grp::bcast0(cidx, &sh_bcast);
       if (cidx >= (uint32_t)P.n_chains) {
