@@ -349,6 +349,20 @@ def make_batch(spec, n, chain_offset, device, data, q0):
     return cb
 
 
+def _traffic(name, chains, iters):
+    """roofline.traffic: DRAM bytes (read + write) of one launch of this workload's kernel, from the committed ncu pass
+    over the bench command (profiles/r02_traffic.json, scripts/traffic_from_ncu.py) -- the bench itself never runs under a
+    profiler.  null when there is no capture of this workload."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as fh:
+            t = json.load(fh)
+        w = t["workloads"][name]
+        return {"traffic": w["traffic_bytes_per_launch"],
+                "traffic_source": "profiles/r02_traffic.json: " + t["source"]}
+    except (OSError, KeyError, ValueError):
+        return {"traffic": None}
+
+
 def gpu_leg(env, name, steps, warmup, chains=None, e2e=True, fp64_peak=None, keep_draws=False):
     """Device-resident timing (+ e2e through pinned host buffers) of one workload; returns the reduced dict on
     every rank."""
@@ -447,7 +461,7 @@ def gpu_leg(env, name, steps, warmup, chains=None, e2e=True, fp64_peak=None, kee
            "params": {k: spec[k] for k in ("integrator", "H0", "delta", "M", "minC", "maxC", "mode")},
            "roofline": {"bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
                         "frac": (ach / fp64_peak) if fp64_peak else None, "flop_per_eval": spec["flop_per_eval"],
-                        "traffic": None,
+                        **_traffic(name, n, iters),
                         **({"flop_per_eval_survey": spec["flop_per_eval_survey"],
                             "achieved_at_survey_flop": ach * spec["flop_per_eval_survey"] / spec["flop_per_eval"],
                             "frac_at_survey_flop": (ach * spec["flop_per_eval_survey"] / spec["flop_per_eval"] / fp64_peak)
