@@ -35,4 +35,13 @@ q0 = 0.05 * rng.standard_normal((3, 756)); q0[:, 0] = 2.4
 run("stock_watson", 756, 3, "R2P", 0.1, 4, {"y": y}, q0, iters=1, minC=3)
 X, yy, beta = datasets.synth_logreg(800, 100, 0)
 run("logreg", 100, 9, "R2P", 0.1, 4, {"X": X, "y": yy, "tau": np.array([1.0])}, beta + 0.05 * rng.standard_normal((9, 100)))
+# chain scheduler (wn_sched.cu): more chains than resident slots, two calls on one handle (the second one is served from
+# the longest-first queue with exclusive warps), and a user plug-in (one warp per chain, d = 200)
+qf = rng.standard_normal((19200, 11)); qf[:, 0] *= 3.0; qf[:, 1:] *= np.exp(0.5 * qf[:, :1])
+with ChainBatch("funnel", 11, 19200, integrator="R2P", H0=0.3, delta=0.3, M=5, seed=3) as cb:
+    cb.set_state(qf)
+    a1 = cb.run(1, draws=True)
+    a2 = cb.run(1, draws=True)
+    assert np.isfinite(a2["draws"]).all()
+print("ok sched", flush=True)
 print("all ok")
