@@ -404,3 +404,19 @@ def test_randomised_configurations(cuda_lib, case):
         assert ok, f"d={d} {integ}: max rel err {err:.3e}"
         assert np.array_equal(out["diag"][:, c][:, EXACT_COLS], dg[:, EXACT_COLS]), f"d={d} {integ}"
         assert int(out["nevalF"][c] + out["nevalB"][c]) == ne
+
+
+@pytest.mark.parametrize("integrator", ["D", "R2P"])
+@pytest.mark.parametrize("d", [6, 1000])
+def test_deep_step_size_search_up_to_c15(cuda_lib, integrator, d):
+    """Maximum sizes of the within-orbit step-size search: a coordinate with sigma = 2e-5 under H0 = 0.5 needs
+    c = 14-15 (16 384-32 768 micro-steps per macro step), far beyond the default maxC = 10 (the reference's transient
+    runs raise maxC to 30: adaptiveIntegrators.py:36-44).  Covers the exact 2^-c step scaling, the per-c check-interval
+    table of the skipped-energy passes and the 32-bit step counters at depth, on the thread-per-chain kernel (d = 6) and
+    on the C2-shaped kernel (d = 1000)."""
+    sigma = np.logspace(-2, 2, d) if d == 1000 else np.array([1.0, 1e-2, 3.0, 0.5, 10.0, 100.0])
+    sigma[1] = 2e-5
+    data = {"inv_var": 1.0 / sigma ** 2}
+    q0 = q0_for(2 if d == 6 else 1, d, seed=11) * sigma
+    dg = check("diag_gauss", q0, integrator, H0=0.5, delta=0.3, M=2, n_iter=1, data=data, maxC=20)
+    assert dg[..., 9].max() >= 14, dg[..., 9]          # max If of the transition
