@@ -67,10 +67,17 @@ static LaunchPlan plan_for() {
   }
 template <int FAM, template <int, int> class T>
 static bool pick_generic(int d, LaunchPlan& p) {
+  // Threads per chain at small d, measured with scripts/small_d_sweep.py (std normal, 131 072 chains; old = the shapes of
+  // round 1: 1 x 12, 4 x 8, 16 x 8): the chains that share a warp sit in different handlers of the state machine most of
+  // the time and are served one after the other, so FEWER chains per warp with shorter per-thread code win as soon as
+  // the handlers are long (D / R2P: d = 10 1.24x, d = 20 1.6x, d = 100 2.5x; fixedLeapFrog d = 20 2.5x, d = 100 1.7x;
+  // package mode d = 100 1.2x, BASELINE config 1 at 65 536 chains 2.78e9 -> 5.18e9 evals/s).  Only the short-handler
+  // kernels (fixedLeapFrog, package mode) at d <= 12 still prefer one thread per chain (8 x 2 there: 0.6-0.8x).
   WN_PICK(1, 2, 128)
-  WN_PICK(1, 6, 128)
-  WN_PICK(4, 4, 128)
-  WN_PICK(16, 4, 128)
+  if constexpr (FAM == FAM_NUTS || FAM == FAM_PKG) { WN_PICK(1, 6, 128) }
+  else { WN_PICK(8, 1, 128) }     // d <= 16: 4 chains per warp, 2 coordinates per thread
+  WN_PICK(16, 1, 128)             // d <= 32: 2 chains per warp
+  WN_PICK(32, 2, 128)             // d <= 128: ONE chain per warp, 4 coordinates per lane
   WN_PICK(32, 8, 128)
   WN_PICK(64, 8, 64)
   WN_PICK(256, 4, 256)
@@ -79,9 +86,10 @@ static bool pick_generic(int d, LaunchPlan& p) {
 }
 template <int FAM, template <int, int> class T>
 static bool pick_warp(int d, LaunchPlan& p) {  // targets that need the chain inside one warp
-  WN_PICK(1, 6, 128)
-  WN_PICK(4, 4, 128)
-  WN_PICK(16, 4, 128)
+  if constexpr (FAM == FAM_NUTS || FAM == FAM_PKG) { WN_PICK(1, 6, 128) }
+  else { WN_PICK(8, 1, 128) }
+  WN_PICK(16, 1, 128)
+  WN_PICK(32, 2, 128)
   WN_PICK(32, 8, 128)
   return false;
 }
@@ -116,15 +124,19 @@ static bool pick_plan_family(const wn_config& c, LaunchPlan& p) {
     case WN_TARGET_FUNNEL:
       if constexpr (FAM == FAM_WPY || FAM == FAM_NUTS) {
         if (c.d <= 16) {
-          // BASELINE config 3 (funnel10, d = 11): 4 threads per chain (8 chains per warp), measured +30 % over
-          // one thread per chain (WN_VARIANT=1; less divergence in the cold path); the control block of every chain in
-          // shared memory (107 instead of 204 registers, twice the resident warps): 1.01e9 against 8.5e8 grad evals/s
-          // (WN_VARIANT=5: control block in registers)
+          // BASELINE config 3 (funnel10, d = 11): 8 threads per chain with 2 coordinates each (4 chains per warp), the
+          // control block of every chain in shared memory, 5 blocks / SM at 92 registers.  The chains of a warp are in
+          // different handlers of the state machine most of the time, so a warp issues nearly every instruction for ONE
+          // of its chains (measured 1.4 chains per issued instruction with 8 chains per warp): fewer chains per warp
+          // with shorter per-thread code win.  Measured at 262 144 chains x 10 transitions, R2P / fixedLeapFrog, ms per
+          // call: 1 thread per chain (WN_VARIANT=1) ~330 / --, 4 threads x 4 coordinates (WN_VARIANT=4, the round-2
+          // default until then) 253 / 99, 8 x 2 (default) 204 / 74, 16 x 2 204 / 79, 32 x 2 243 / 87
           const char* v = getenv("WN_VARIANT");
           const int var = v ? atoi(v) : 0;
           if (var == 1 && c.d <= 12) p = plan_plain<FAM, FunnelT, 1, 6, 128, 1>();
           else if (var == 5) p = plan_plain<FAM, FunnelT, 4, 2, 128, 1>();
-          else p = plan_plain<FAM, FunnelT, 4, 2, 128, 4, true>();
+          else if (var == 4) p = plan_plain<FAM, FunnelT, 4, 2, 128, 4, true>();
+          else p = plan_plain<FAM, FunnelT, 8, 1, 128, 5, true>();
           return true;
         }
       }
