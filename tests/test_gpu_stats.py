@@ -232,7 +232,9 @@ def test_longest_first_queue_order_is_a_hint_only(cuda_lib, mode):
     call's evaluation counts.  More chains than resident slots, three calls of three transitions against ONE call of
     nine (which has no history, hence the natural order): bit-identical draws, counters and final states."""
     from walnuts_b200 import ChainBatch
-    n, d = 40000, 11
+    # more chains than resident chain slots (walnutspy: 148 SMs x 5 blocks x 16 chains; package mode, one thread per
+    # chain: up to 148 x 4 x 128)
+    n, d = (40000 if mode == "walnutspy" else 100000), 11
     rng = np.random.default_rng(12)
     q0 = rng.standard_normal((n, d))
     q0[:, 0] *= 3.0
