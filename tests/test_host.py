@@ -177,3 +177,29 @@ def test_bench_workloads_are_the_baseline_configs():
     s = bench.sigma_vec()
     assert s.shape == (1000,) and np.isclose(s.min(), 1e-2) and np.isclose(s.max(), 1e2)
     assert np.isclose(s[0], 1e-2) and np.isclose(s[bench.MONITOR - 1], 1e2)      # monitored coordinates span the range
+
+
+def test_roofline_traffic_comes_from_the_committed_ncu_capture(tmp_path):
+    """bench.py never runs under a profiler: roofline.traffic is read from profiles/r02_traffic.json, which
+    scripts/traffic_from_ncu.py writes from the CSV of one ncu pass over the bench command."""
+    import csv, json, subprocess, sys
+    import bench
+    t = bench._traffic("c2", 65536, 1)
+    assert t["traffic"] and t["traffic"] > 1e9 and "ncu" in t["traffic_source"]
+    assert bench._traffic("no_such_workload", 1, 1) == {"traffic": None}
+    # the parser on a synthetic log: warm-up + two timed launches per kernel group -> average of launches 2 and 3
+    src, dst = tmp_path / "t.csv", tmp_path / "t.json"
+    hdr = ["ID", "Process ID", "Process Name", "Host Name", "Kernel Name", "Context", "Stream", "Block Size", "Grid Size",
+           "Device", "CC", "Section Name", "Metric Name", "Metric Unit", "Metric Value"]
+    with open(src, "w", newline="") as fh:
+        w = csv.writer(fh, quoting=csv.QUOTE_ALL)
+        w.writerow(hdr)
+        for i, rd in enumerate((5, 10, 30)):
+            for name, val in (("dram__bytes_read.sum", rd), ("dram__bytes_write.sum", 2 * rd), ("gpu__time_duration.sum", 7)):
+                w.writerow([i, 1, "python", "h", "void walnutspy_kernel<DiagT, 128, 4, 128, 4, 0, 0, 2, 0, 0>(RunParams)", 1, 7,
+                            "(128, 1, 1)", "(592, 1, 1)", 0, "10.0", "s", name, "Mbyte" if "dram" in name else "ns", val])
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run([sys.executable, os.path.join(root, "scripts", "traffic_from_ncu.py"), str(src), str(dst)], check=True,
+                   capture_output=True)
+    out = json.load(open(dst))["workloads"]["c2"]
+    assert out["dram_read_bytes_per_launch"] == 20e6 and out["traffic_bytes_per_launch"] == 60e6
