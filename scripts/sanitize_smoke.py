@@ -24,6 +24,9 @@ run("diag_gauss", 1000, 5, "R2P", 0.5, 4, {"inv_var": 1 / sig ** 2}, rng.standar
 run("std_normal", 300, 6, "fixed", 0.2, 6)                                                                        # NUTS_FAST, G = 32, 4 chains/block
 run("std_normal", 2000, 3, "fixed", 0.1, 5)                                                                       # NUTS_FAST, G = 256
 run("std_normal", 100, 6, "fixed", 0.3, 6)                                                                        # flat loop, compile-time fixed
+run("std_normal", 10, 40, "R2P", 0.4, 6)                                                                        # 8 threads x 2 coordinates
+run("std_normal", 24, 40, "D", 0.4, 6)                                                                          # 16 threads x 2 coordinates
+run("std_normal", 100, 12, "R2P", 0.3, 6)                                                                       # one chain per warp, 4 coordinates per lane
 run("funnel", 11, 40, "R2P", 0.3, 8)                                                                              # control block in smem
 run("funnel", 11, 40, "fixed", 0.3, 8)
 P = np.eye(100) * 2 + 0.01
