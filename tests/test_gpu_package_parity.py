@@ -93,3 +93,19 @@ def test_fp64_peak_microbenchmark(cuda_lib):
     from walnuts_b200 import fp64_peak
     peak = fp64_peak(0)
     assert 5e12 < peak < 6e13        # B200: ~34 TFLOP/s measured, 37 nominal
+
+
+@pytest.mark.parametrize("d", [7, 24, 40, 200])
+def test_package_small_macro_step_ell_zero_defect_all_kernel_shapes(cuda_lib, d):
+    """A macro step so small that the stable micro-step count is 1: choose_micro_steps then draws from {0, 1, 2}
+    (walnuts.py:194), and ell = 0 makes the step size infinite and the orbit NaN (defect B3, reproduced with
+    compat=True).  Covers that path on every package-kernel shape: one thread per chain (d = 7), 16 threads (24), one
+    warp per chain with 4 and 16 coordinates per lane (40, 200)."""
+    n_chains, n_iter, seed = 6, 8, 31
+    theta0 = 0.4 * np.random.default_rng(1).standard_normal((n_chains, d))
+    draws = cuda_walnuts("std_normal", theta0, np.ones(d), 0.25, 5, 0.3, n_iter, seed, compat=True)
+    for c in range(n_chains):
+        ref = po.walnuts(seed, c, theta0[c], ot.standard_normal_lpdf, ot.standard_normal_grad, np.ones(d), 0.25, 5, 0.3,
+                         0, n_iter, compat=True)
+        ok, err = close(draws[c], ref)
+        assert ok, f"d = {d}, chain {c}: max rel err {err:.3e}"

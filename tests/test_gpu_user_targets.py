@@ -165,5 +165,13 @@ def test_user_target_d200_warp_per_chain(cuda_lib):
         ok, err = close(s1, s2, axis=-2)
         assert ok, (ig, err)
         assert np.array_equal(d1[..., EXACT], d2[..., EXACT]), ig
+    # package semantics on the same plug-in (package_kernel<UserWarpT, ...>), incl. a macro step small enough for the
+    # ell = 0 defect path (walnuts.py:194)
+    bi = wb.targets.diag_gauss(sigma)
+    for macro in (0.35, 0.02):
+        p1 = wb.walnuts(None, q0, tg, tg, np.ones(d), macro, 5, 0.3, 0, 6, seed=9)
+        p2 = wb.walnuts(None, q0, bi, bi, np.ones(d), macro, 5, 0.3, 0, 6, seed=9)
+        ok, err = close(p1, p2, axis=-1)
+        assert ok, (macro, err)
     with pytest.raises(ValueError):
         wb.targets.cuda_target(src, 513)

@@ -44,7 +44,7 @@ struct UserWarpT {
   static constexpr bool LAZY_ENERGY = false;
   static constexpr bool COOP = false;
   static constexpr int DPAD = 2 * G * E2;
-  static_assert(G == 32 && DPAD >= WN_USER_D, "user targets with d > 64 run one warp per chain");
+  static_assert(G == 32 && DPAD >= WN_USER_D, "warp layout: 32 lanes x 2 E2 coordinates must cover d");
   __host__ __device__ static constexpr int smem_doubles(int NT) { return (NT / 32) * 2 * DPAD; }
   const double* data;
   int nd;
@@ -73,8 +73,12 @@ struct UserWarpT {
 };
 
 constexpr int WN_USER_E2 = (WN_USER_D + 1) / 2;
+#ifdef WN_USER_FORCE_WARP          // measurement: the warp layout at any d (scripts/user_layout_sweep.py)
+constexpr bool WN_USER_WARP = true;
+#else
 constexpr bool WN_USER_WARP = WN_USER_D > 64;
-constexpr int WN_USER_WE2 = (WN_USER_D <= 256) ? 4 : 8;     // 32 lanes x 8 / 16 coordinates
+#endif
+constexpr int WN_USER_WE2 = (WN_USER_D <= 64) ? 1 : (WN_USER_D <= 256) ? 4 : 8;     // 32 lanes x 2 / 8 / 16 coordinates
 
 // (a template, so that only the layout in use is instantiated)
 template <bool WARP>
